@@ -1,0 +1,161 @@
+/*
+ * kzg_b200.h -- C ABI of the B200 blob path (libkzg_b200.so).
+ *
+ * Drop-in boundary for the data-parallel part of pawanjay176/kzg_rust.  The reference has no
+ * FFI seam of its own for this path (its only foreign calls are into blst); the entry points
+ * below are what `impl Kzg` (reference src/kzg.rs:983-1079) binds to once its bodies are
+ * re-routed, plus batched forms.  Each declaration cites the reference item it replaces.
+ * INTEGRATION.md shows the Rust side (`extern "C"` block + the `Kzg` methods calling it).
+ *
+ * Conventions
+ *   - All buffers are caller-owned, contiguous, fixed-size records: blobs n x BYTES_PER_BLOB,
+ *     commitments / proofs n x 48, field elements n x 32 (big-endian, as in the reference).
+ *     Byte-length validation stays in the host wrapper types (reference `Blob::from_bytes`
+ *     src/kzg.rs:160-173, `Bytes48::from_bytes` :130-141, `Bytes32::from_bytes` :107-117).
+ *   - Return value: KZG_B200_OK or an error code that mirrors reference `enum Error`
+ *     (src/kzg.rs:10-22) plus one CUDA/runtime code.  Batched calls also fill status[i] per
+ *     blob, so one bad blob does not poison the batch; the single-blob Rust methods map a
+ *     non-zero status[0] to `Err`.
+ *   - A context plays the role of `KzgSettings` (src/kzg.rs:27-40) and owns all device memory
+ *     (the precomputed multiples of the Lagrange points, roots of unity, workspaces).  It is
+ *     bound to one GPU; multi-GPU use is one context (and one process) per GPU with the blob
+ *     range sharded by the caller.  Calls on one context are serialised internally, so it may
+ *     be shared between host threads like `&KzgSettings`.
+ *   - There is no CPU fallback: without a usable CUDA device ctx creation fails.
+ */
+#ifndef KZG_B200_H
+#define KZG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* reference src/consts.rs:5-37 */
+#define KZG_B200_BYTES_PER_FIELD_ELEMENT 32
+#define KZG_B200_BYTES_PER_COMMITMENT 48
+#define KZG_B200_BYTES_PER_PROOF 48
+#define KZG_B200_BYTES_PER_G1 48
+#define KZG_B200_BYTES_PER_G2 96
+#define KZG_B200_NUM_G2_POINTS 65
+
+/* reference `enum Error`, src/kzg.rs:10-22 (+ KZG_B200_CUDA_ERROR) */
+enum {
+    KZG_B200_OK = 0,
+    KZG_B200_BAD_ARGS = 1,
+    KZG_B200_INTERNAL_ERROR = 2,
+    KZG_B200_INVALID_BYTES_LENGTH = 3,
+    KZG_B200_INVALID_HEX_FORMAT = 4,
+    KZG_B200_INVALID_TRUSTED_SETUP = 5,
+    KZG_B200_CUDA_ERROR = 6
+};
+
+typedef struct kzg_b200_ctx kzg_b200_ctx;
+
+/*
+ * Replaces `Kzg::load_trusted_setup` (src/kzg.rs:1005-1010 -> load_trusted_setup :833-899).
+ *   g1_lagrange: n1 x 48 B compressed G1 points, Lagrange form, FILE order (the library
+ *                applies the bit-reversal permutation of src/kzg.rs:895-896 itself)
+ *   g2_monomial: n2 x 96 B compressed G2 points; n2 must be 65
+ *   n1:          FIELD_ELEMENTS_PER_BLOB of the preset: 4096 (kzg_mainnet) or 4 (kzg_minimal)
+ *   device:      CUDA device ordinal
+ *   window_bits: signed-digit window of the precomputed table, 0 = pick the largest that
+ *                fits the device's free memory (15 on a 180 GB B200, 102 GiB of table)
+ */
+int kzg_b200_ctx_create(const uint8_t *g1_lagrange, size_t n1, const uint8_t *g2_monomial, size_t n2,
+                        int device, int window_bits, kzg_b200_ctx **out);
+
+/* Replaces `Kzg::load_trusted_setup_file` (src/kzg.rs:995-999 -> :906-979): text file
+ * "n1\nn2\n" followed by n1 + n2 hex lines. */
+int kzg_b200_ctx_create_from_file(const char *path, int device, int window_bits, kzg_b200_ctx **out);
+
+void kzg_b200_ctx_destroy(kzg_b200_ctx *ctx);
+
+/* FIELD_ELEMENTS_PER_BLOB of the context's preset (src/consts.rs:13). */
+size_t kzg_b200_field_elements_per_blob(const kzg_b200_ctx *ctx);
+/* Signed-digit window width the context's table was built with. */
+int kzg_b200_window_bits(const kzg_b200_ctx *ctx);
+
+/*
+ * Replaces `Kzg::blob_to_kzg_commitment` (src/kzg.rs:1013-1018 -> :401-406), batched.
+ * HOST pointers.  out: n x 48 B.  status: n x int32 (KZG_B200_OK / KZG_B200_BAD_ARGS for a
+ * non-canonical field element, src/utils.rs:262-275).
+ */
+int kzg_b200_blob_to_kzg_commitment_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, size_t n, uint8_t *out,
+                                          int32_t *status);
+
+/*
+ * Replaces `Kzg::compute_blob_kzg_proof` (src/kzg.rs:1030-1036 -> :533-544), batched.
+ * status[i] = KZG_B200_BAD_ARGS for a non-canonical blob element or an invalid commitment
+ * (bad encoding, not on the curve, not in G1; src/utils.rs:282-315).
+ */
+int kzg_b200_compute_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments,
+                                          size_t n, uint8_t *proofs_out, int32_t *status);
+
+/*
+ * Replaces `Kzg::compute_kzg_proof` (src/kzg.rs:1021-1027 -> :446-457), batched: proof of
+ * evaluation at the caller's z (n x 32 B big-endian, must be canonical).  y_out: n x 32 B.
+ */
+int kzg_b200_compute_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *z, size_t n,
+                                     uint8_t *proofs_out, uint8_t *y_out, int32_t *status);
+
+/*
+ * Replaces `Kzg::verify_blob_kzg_proof_batch` (src/kzg.rs:1066-1078 -> :637-693) and, with
+ * n == 1, `Kzg::verify_blob_kzg_proof` (:1050-1063 -> :547-569).  n == 0 -> *ok = 1.
+ * Returns KZG_B200_BAD_ARGS (and leaves *ok = 0) if any blob, commitment or proof is
+ * malformed, like the `?` short-circuit at src/kzg.rs:671-683.
+ */
+int kzg_b200_verify_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments,
+                                         const uint8_t *proofs, size_t n, int *ok);
+
+/*
+ * Two-phase form of the batch verification for multi-GPU sharding.
+ * Phase A (per shard): validate, z_i and y_i.  zy_out: n x 64 B (z_i || y_i, big-endian).
+ * The caller concatenates the shards' records in blob order, computes r with
+ * kzg_b200_compute_r (reference `compute_r_powers`, src/utils.rs:426-474), then
+ * Phase B (per shard): partial sums with r^(first_index + i):
+ *   out_partial = A_g (96 B uncompressed affine x||y or 0x40.. for infinity) || B_g (96 B) || s_g (32 B)
+ *   with A_g = sum r^i proof_i, B_g = sum r^i C_i + sum r^i z_i proof_i, s_g = sum r^i y_i.
+ * kzg_b200_verify_finish adds the partial sums of all shards and runs the final check
+ * e(A, [tau]G2) == e(B - [s]G1, G2) on the host (reference src/kzg.rs:618-625).
+ */
+int kzg_b200_verify_phase_a(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments,
+                            const uint8_t *proofs, size_t n, uint8_t *zy_out);
+int kzg_b200_compute_r(const kzg_b200_ctx *ctx, const uint8_t *commitments, const uint8_t *zy,
+                       const uint8_t *proofs, size_t n_total, uint8_t r_out[32]);
+int kzg_b200_verify_phase_b(kzg_b200_ctx *ctx, const uint8_t *commitments, const uint8_t *zy,
+                            const uint8_t *proofs, size_t n, const uint8_t r[32], uint64_t first_index,
+                            uint8_t partial_out[224]);
+int kzg_b200_verify_finish(const kzg_b200_ctx *ctx, const uint8_t *partials, size_t n_partials, int *ok);
+
+/*
+ * Device-resident forms (inputs and outputs already in this context's GPU memory; used by
+ * pipelines that produce blobs on the device and by bench.py's HBM-resident measurement).
+ * Asynchronous on the context's stream; kzg_b200_synchronize waits for completion.
+ */
+int kzg_b200_blob_to_kzg_commitment_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, size_t n, uint8_t *d_out,
+                                           int32_t *d_status);
+int kzg_b200_compute_blob_kzg_proof_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments,
+                                           size_t n, uint8_t *d_proofs_out, int32_t *d_status);
+int kzg_b200_synchronize(kzg_b200_ctx *ctx);
+/* the CUDA stream (cudaStream_t) the context launches on, for event timing */
+void *kzg_b200_stream(kzg_b200_ctx *ctx);
+/* number of kernel launches issued by this context so far (bench.py reports the delta) */
+uint64_t kzg_b200_launch_count(const kzg_b200_ctx *ctx);
+
+/* Host final check used by verify (stand-in for blst's pairing, reference src/utils.rs:189-214):
+ * e(a1, a2) == e(b1, b2) on compressed points.  Exposed for tests. */
+int kzg_b200_pairings_verify(const uint8_t a1[48], const uint8_t a2[96], const uint8_t b1[48],
+                             const uint8_t b2[96], int *ok);
+
+/* Micro-benchmarks used by bench.py to measure the integer-multiply roofline on the device
+ * the context is bound to: issue rate of independent 32-bit IMADs (ops/s) and of full Fp
+ * Montgomery multiplications (mul/s).  */
+int kzg_b200_measure_peaks(kzg_b200_ctx *ctx, double *imad_per_s, double *fp_mul_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,243 @@
+// bigint.cuh -- Montgomery field arithmetic on 32-bit limbs for sm_100a (and, for the
+// host-side parts of the library and for CPU unit tests, the same code on the host).
+//
+// Replaces, for the blob path, the blst field calls listed in SURVEY.md section 2b:
+// blst_fr_add/sub/mul/sqr, blst_fr_eucl_inverse, blst_fr_from_scalar/blst_scalar_from_fr
+// (reference src/utils.rs:13-123, 230-275) and the Fp arithmetic underneath every
+// blst_p1_* call (reference src/utils.rs:126-140, 221-227, 282-410).
+//
+// Device path: carry chains of mad.lo.cc / madc.hi.cc (IMAD on the FMA pipe) written as
+// inline PTX.  A 32x32->64 product is two IMAD issue slots; one Fp multiplication is
+// 2*(12*12) + 2*(12*12) + 12 = 588 of them, one Fr multiplication 2*64 + 2*64 + 8 = 264.
+// Products are accumulated into two interleaved accumulators ("even"/"odd" 64-bit
+// columns) so that no carry ever has to ripple further than one chain.
+//
+// Host path: each PTX primitive has a C++ stand-in with an explicit carry variable, so the
+// algorithms are byte-for-byte the same and can be checked on a CPU.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define KZG_HD __host__ __device__ __forceinline__
+#define KZG_D __device__ __forceinline__
+#else
+#define KZG_HD inline
+#define KZG_D inline
+#endif
+
+namespace kzg {
+
+// ------------------------------------------------------------------ carry primitives
+// `cc` is the emulated carry flag on the host; on the device the hardware flag is used and
+// the argument is dead.
+#if defined(__CUDA_ARCH__)
+KZG_HD uint32_t add_cc(uint32_t a, uint32_t b, uint32_t &) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+KZG_HD uint32_t addc_cc(uint32_t a, uint32_t b, uint32_t &) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+KZG_HD uint32_t addc(uint32_t a, uint32_t b, uint32_t &) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+KZG_HD uint32_t sub_cc(uint32_t a, uint32_t b, uint32_t &) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+KZG_HD uint32_t subc_cc(uint32_t a, uint32_t b, uint32_t &) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+KZG_HD uint32_t subc(uint32_t a, uint32_t b, uint32_t &) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+KZG_HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c, uint32_t &) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+KZG_HD uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c, uint32_t &) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+KZG_HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c, uint32_t &) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+KZG_HD uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+#else
+KZG_HD uint32_t add_cc(uint32_t a, uint32_t b, uint32_t &cc) { uint64_t s = (uint64_t)a + b; cc = (uint32_t)(s >> 32); return (uint32_t)s; }
+KZG_HD uint32_t addc_cc(uint32_t a, uint32_t b, uint32_t &cc) { uint64_t s = (uint64_t)a + b + cc; cc = (uint32_t)(s >> 32); return (uint32_t)s; }
+KZG_HD uint32_t addc(uint32_t a, uint32_t b, uint32_t &cc) { return a + b + cc; }
+KZG_HD uint32_t sub_cc(uint32_t a, uint32_t b, uint32_t &cc) { uint64_t s = (uint64_t)a - b; cc = (uint32_t)(s >> 63); return (uint32_t)s; }
+KZG_HD uint32_t subc_cc(uint32_t a, uint32_t b, uint32_t &cc) { uint64_t s = (uint64_t)a - b - cc; cc = (uint32_t)(s >> 63); return (uint32_t)s; }
+KZG_HD uint32_t subc(uint32_t a, uint32_t b, uint32_t &cc) { return a - b - cc; }
+KZG_HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c, uint32_t &cc) { uint64_t s = (uint64_t)(uint32_t)((uint64_t)a * b) + c; cc = (uint32_t)(s >> 32); return (uint32_t)s; }
+KZG_HD uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c, uint32_t &cc) { uint64_t s = (uint64_t)(uint32_t)((uint64_t)a * b) + c + cc; cc = (uint32_t)(s >> 32); return (uint32_t)s; }
+KZG_HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c, uint32_t &cc) { uint64_t s = (((uint64_t)a * b) >> 32) + c + cc; cc = (uint32_t)(s >> 32); return (uint32_t)s; }
+KZG_HD uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+#endif
+
+// acc[0 .. 2L] += sum_{k<L} x[2k] * m * 2^(64k).  One carry chain; the carry out of the
+// top pair lands in acc[2L] when CARRY_OUT (the callers know when it is provably zero).
+template <int L, bool CARRY_OUT>
+KZG_HD void mad_row(uint32_t *acc, const uint32_t *x, uint32_t m) {
+    uint32_t cc = 0;
+    acc[0] = mad_lo_cc(x[0], m, acc[0], cc);
+    acc[1] = madc_hi_cc(x[0], m, acc[1], cc);
+#pragma unroll
+    for (int k = 1; k < L; k++) {
+        acc[2 * k] = madc_lo_cc(x[2 * k], m, acc[2 * k], cc);
+        acc[2 * k + 1] = madc_hi_cc(x[2 * k], m, acc[2 * k + 1], cc);
+    }
+    if (CARRY_OUT) acc[2 * L] = addc(acc[2 * L], 0, cc);
+}
+
+// ------------------------------------------------------------------ the field template
+// P supplies: N (limbs, even), mod(i), n0, r1(i) (Montgomery one), r2(i) (R^2 mod m).
+template <class P>
+struct alignas(16) Fe {
+    static constexpr int N = P::N;
+    uint32_t l[N];
+};
+
+template <class P> KZG_HD bool fe_is_zero(const Fe<P> &a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) o |= a.l[i];
+    return o == 0;
+}
+template <class P> KZG_HD bool fe_eq(const Fe<P> &a, const Fe<P> &b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) o |= a.l[i] ^ b.l[i];
+    return o == 0;
+}
+template <class P> KZG_HD void fe_set_zero(Fe<P> &a) {
+#pragma unroll
+    for (int i = 0; i < P::N; i++) a.l[i] = 0;
+}
+template <class P> KZG_HD Fe<P> fe_one() {
+    Fe<P> r;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) r.l[i] = P::r1(i);
+    return r;
+}
+// r = a - mod if a >= mod (a < 2*mod, plus an optional incoming carry bit)
+template <class P> KZG_HD void fe_reduce_once(Fe<P> &a, uint32_t top) {
+    uint32_t d[P::N], cc = 0;
+    d[0] = sub_cc(a.l[0], P::mod(0), cc);
+#pragma unroll
+    for (int i = 1; i < P::N; i++) d[i] = subc_cc(a.l[i], P::mod(i), cc);
+    uint32_t borrow = subc(top, 0, cc);  // top - borrow: 0xffffffff iff (top:a) < mod
+    bool keep = (borrow != 0) && (top == 0);
+    // keep a when a < mod: that is borrow out with top == 0
+#pragma unroll
+    for (int i = 0; i < P::N; i++) a.l[i] = keep ? a.l[i] : d[i];
+}
+template <class P> KZG_HD void fe_add(Fe<P> &r, const Fe<P> &a, const Fe<P> &b) {
+    uint32_t cc = 0;
+    Fe<P> t;
+    t.l[0] = add_cc(a.l[0], b.l[0], cc);
+#pragma unroll
+    for (int i = 1; i < P::N; i++) t.l[i] = addc_cc(a.l[i], b.l[i], cc);
+    uint32_t top = addc(0, 0, cc);
+    fe_reduce_once(t, top);
+    r = t;
+}
+template <class P> KZG_HD void fe_sub(Fe<P> &r, const Fe<P> &a, const Fe<P> &b) {
+    uint32_t cc = 0;
+    Fe<P> t;
+    t.l[0] = sub_cc(a.l[0], b.l[0], cc);
+#pragma unroll
+    for (int i = 1; i < P::N; i++) t.l[i] = subc_cc(a.l[i], b.l[i], cc);
+    uint32_t borrow = subc(0, 0, cc);  // 0 or 0xffffffff
+    uint32_t c2 = 0;
+    r.l[0] = add_cc(t.l[0], P::mod(0) & borrow, c2);
+#pragma unroll
+    for (int i = 1; i < P::N; i++) r.l[i] = addc_cc(t.l[i], P::mod(i) & borrow, c2);
+}
+template <class P> KZG_HD void fe_neg(Fe<P> &r, const Fe<P> &a) {
+    Fe<P> z;
+    fe_set_zero(z);
+    fe_sub(r, z, a);
+}
+template <class P> KZG_HD void fe_dbl(Fe<P> &r, const Fe<P> &a) { fe_add(r, a, a); }
+
+// Montgomery product: separated operand scanning into even/odd accumulators, then an
+// interleaved-carry reduction.  Inputs < mod, output < mod.
+template <class P> KZG_HD void fe_mul(Fe<P> &r, const Fe<P> &a, const Fe<P> &b) {
+    constexpr int N = P::N, H = P::N / 2;
+    // value = sum ev[k] 2^(32k) + sum od[k] 2^(32(k+1))
+    uint32_t ev[2 * N + 2], od[2 * N + 2];
+#pragma unroll
+    for (int i = 0; i < 2 * N + 2; i++) { ev[i] = 0; od[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        if ((i & 1) == 0) {
+            mad_row<H, true>(ev + i, a.l, b.l[i]);
+            mad_row<H, true>(od + i, a.l + 1, b.l[i]);
+        } else {
+            mad_row<H, true>(od + i - 1, a.l, b.l[i]);
+            mad_row<H, (true)>(ev + i + 1, a.l + 1, b.l[i]);
+        }
+    }
+    uint32_t mp[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) mp[i] = P::mod(i);
+    uint32_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        uint32_t t = ev[i] + (i > 0 ? od[i - 1] : 0u) + carry;
+        uint32_t m = mul_lo(t, P::n0);
+        if ((i & 1) == 0) {
+            mad_row<H, true>(ev + i, mp, m);
+            mad_row<H, true>(od + i, mp + 1, m);
+        } else {
+            mad_row<H, true>(od + i - 1, mp, m);
+            mad_row<H, true>(ev + i + 1, mp + 1, m);
+        }
+        // limb i is now 0 mod 2^32; what is left of it is a carry of 0, 1 or 2
+        uint32_t cc = 0, c1, c2;
+        uint32_t s = add_cc(ev[i], (i > 0 ? od[i - 1] : 0u), cc);
+        c1 = addc(0, 0, cc);
+        (void)add_cc(s, carry, cc);
+        c2 = addc(0, 0, cc);
+        carry = c1 + c2;
+    }
+    Fe<P> t;
+    uint32_t cc = 0;
+    {
+        uint32_t s = add_cc(ev[N], od[N - 1], cc);
+        uint32_t c1 = addc(0, 0, cc);
+        t.l[0] = add_cc(s, carry, cc);
+        uint32_t c2 = addc(0, 0, cc);
+        carry = c1 + c2;
+    }
+#pragma unroll
+    for (int k = 1; k < N; k++) {
+        uint32_t s = add_cc(ev[N + k], od[N + k - 1], cc);
+        uint32_t c1 = addc(0, 0, cc);
+        t.l[k] = add_cc(s, carry, cc);
+        uint32_t c2 = addc(0, 0, cc);
+        carry = c1 + c2;
+    }
+    fe_reduce_once(t, 0);
+    r = t;
+}
+template <class P> KZG_HD void fe_sqr(Fe<P> &r, const Fe<P> &a) { fe_mul(r, a, a); }
+
+template <class P> KZG_HD void fe_to_mont(Fe<P> &r, const Fe<P> &a) {
+    Fe<P> r2;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) r2.l[i] = P::r2(i);
+    fe_mul(r, a, r2);
+}
+template <class P> KZG_HD void fe_from_mont(Fe<P> &r, const Fe<P> &a) {
+    Fe<P> one;
+    fe_set_zero(one);
+    one.l[0] = 1;
+    fe_mul(r, a, one);
+}
+// r = a^e, e given as NE little-endian 32-bit words (not unrolled: code size)
+template <class P> KZG_HD void fe_pow(Fe<P> &r, const Fe<P> &a, const uint32_t *e, int ne) {
+    Fe<P> acc = fe_one<P>();
+    bool started = false;
+#pragma unroll 1
+    for (int i = ne * 32 - 1; i >= 0; i--) {
+        if (started) fe_sqr(acc, acc);
+        if ((e[i >> 5] >> (i & 31)) & 1) {
+            if (started) fe_mul(acc, acc, a);
+            else { acc = a; started = true; }
+        }
+    }
+    r = acc;
+}
+// canonical (non-Montgomery) a >= b ?
+template <int N> KZG_HD bool limbs_geq(const uint32_t *a, const uint32_t *b) {
+    uint32_t cc = 0;
+    (void)sub_cc(a[0], b[0], cc);
+#pragma unroll
+    for (int i = 1; i < N; i++) (void)subc_cc(a[i], b[i], cc);
+    uint32_t borrow = subc(0, 0, cc);
+    return borrow == 0;
+}
+
+}  // namespace kzg

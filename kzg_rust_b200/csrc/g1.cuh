@@ -1,0 +1,222 @@
+// g1.cuh -- BLS12-381 G1 on the device (and host): affine points for the batched
+// additions of the MSM, Jacobian points for the few per-point scalar multiplications, and
+// the ZCash (de)compression that blst_p1_compress / blst_p1_uncompress implement
+// (reference src/utils.rs:221-227, 282-315).
+#pragma once
+#include "fields.cuh"
+
+namespace kzg {
+
+// Affine point, Montgomery coordinates, 96 B.  Infinity is encoded by an x whose top limb
+// is 0xffffffff (no field element looks like that: p < 2^381).
+struct alignas(16) g1_affine_t {
+    fp_t x, y;
+};
+KZG_HD bool g1a_is_inf(const g1_affine_t &p) { return p.x.l[11] == 0xffffffffu; }
+KZG_HD bool fp_is_inf_marker(const fp_t &x) { return x.l[11] == 0xffffffffu; }
+KZG_HD void g1a_set_inf(g1_affine_t &p) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) { p.x.l[i] = 0xffffffffu; p.y.l[i] = 0; }
+}
+
+// ------------------------------------------------------------------ one step of a batched affine addition
+// R = P1 + P2 is computed in two passes around one shared inversion (Montgomery's trick):
+//   pass 1: den = add_denominator(...)       -> multiplied into the running product
+//   pass 2: add_finish(..., 1/den)           -> the sum
+// Every case of the group law is exact:
+//   P1 or P2 infinity -> den = 1, R = the other operand
+//   x1 != x2          -> den = x2 - x1,  lambda = (y2 - y1)/den
+//   P1 == P2          -> den = 2 y1,     lambda = 3 x1^2/den      (y1 != 0: the curve has odd order)
+//   P1 == -P2         -> den = 1, R = infinity
+enum { ADD_GENERIC = 0, ADD_TAKE_P2 = 1, ADD_TAKE_P1 = 2, ADD_DOUBLE = 3, ADD_CANCEL = 4 };
+
+// y1/y2 are only read when x1 == x2 (the caller passes loaders so the common case does
+// not touch them in pass 1).
+template <class LoadY1, class LoadY2>
+KZG_HD int add_denominator(fp_t &den, const fp_t &x1, const fp_t &x2, LoadY1 load_y1, LoadY2 load_y2) {
+    if (fp_is_inf_marker(x1)) { den = fe_one<FpParams>(); return ADD_TAKE_P2; }
+    if (fp_is_inf_marker(x2)) { den = fe_one<FpParams>(); return ADD_TAKE_P1; }
+    fe_sub(den, x2, x1);
+    if (!fe_is_zero(den)) return ADD_GENERIC;
+    fp_t y1, y2;
+    load_y1(y1);
+    load_y2(y2);
+    if (fe_eq(y1, y2) && !fe_is_zero(y1)) { fe_dbl(den, y1); return ADD_DOUBLE; }
+    den = fe_one<FpParams>();
+    return ADD_CANCEL;
+}
+// inv = 1/den for this addition
+KZG_HD void add_finish(g1_affine_t &r, int kind, const g1_affine_t &p1, const g1_affine_t &p2, const fp_t &inv) {
+    if (kind == ADD_TAKE_P2) { r = p2; return; }
+    if (kind == ADD_TAKE_P1) { r = p1; return; }
+    if (kind == ADD_CANCEL) { g1a_set_inf(r); return; }
+    fp_t num, lam, t;
+    if (kind == ADD_DOUBLE) {
+        fe_sqr(t, p1.x);
+        fe_dbl(num, t);
+        fe_add(num, num, t);
+    } else {
+        fe_sub(num, p2.y, p1.y);
+    }
+    fe_mul(lam, num, inv);
+    fe_sqr(t, lam);
+    fe_sub(t, t, p1.x);
+    fe_sub(t, t, p2.x);  // x3 (p2.x == p1.x when doubling)
+    fp_t u;
+    fe_sub(u, p1.x, t);
+    fe_mul(u, lam, u);
+    fe_sub(r.y, u, p1.y);
+    r.x = t;
+}
+
+// ------------------------------------------------------------------ Jacobian (Z == 0 is infinity)
+struct g1_jac_t {
+    fp_t x, y, z;
+};
+KZG_HD bool g1j_is_inf(const g1_jac_t &p) { return fe_is_zero(p.z); }
+KZG_HD void g1j_set_inf(g1_jac_t &p) { fe_set_zero(p.x); fe_set_zero(p.y); fe_set_zero(p.z); }
+KZG_HD void g1j_from_affine(g1_jac_t &r, const g1_affine_t &a) {
+    if (g1a_is_inf(a)) { g1j_set_inf(r); return; }
+    r.x = a.x; r.y = a.y; r.z = fe_one<FpParams>();
+}
+KZG_HD void g1j_dbl(g1_jac_t &r, const g1_jac_t &p) {
+    // a = 0 doubling; infinity maps to infinity because Z3 = 2 Y Z
+    fp_t A, B, C, D, E, F, t;
+    fe_sqr(A, p.x);
+    fe_sqr(B, p.y);
+    fe_sqr(C, B);
+    fe_add(t, p.x, B); fe_sqr(t, t); fe_sub(t, t, A); fe_sub(t, t, C); fe_dbl(D, t);
+    fe_dbl(E, A); fe_add(E, E, A);
+    fe_sqr(F, E);
+    fp_t z3;
+    fe_mul(z3, p.y, p.z); fe_dbl(z3, z3);
+    fe_dbl(t, D); fe_sub(r.x, F, t);
+    fe_sub(t, D, r.x); fe_mul(t, E, t);
+    fe_dbl(C, C); fe_dbl(C, C); fe_dbl(C, C);
+    fe_sub(r.y, t, C);
+    r.z = z3;
+}
+// r = p + q (q affine, not infinity), complete
+KZG_HD void g1j_add_affine(g1_jac_t &r, const g1_jac_t &p, const fp_t &qx, const fp_t &qy) {
+    if (g1j_is_inf(p)) { r.x = qx; r.y = qy; r.z = fe_one<FpParams>(); return; }
+    fp_t z1z1, u2, s2, h, hh, i, j, rr, v, t;
+    fe_sqr(z1z1, p.z);
+    fe_mul(u2, qx, z1z1);
+    fe_mul(s2, qy, p.z); fe_mul(s2, s2, z1z1);
+    if (fe_eq(p.x, u2)) {
+        if (fe_eq(p.y, s2)) { g1j_dbl(r, p); return; }
+        g1j_set_inf(r);
+        return;
+    }
+    fe_sub(h, u2, p.x);
+    fe_sqr(hh, h);
+    fe_dbl(i, hh); fe_dbl(i, i);
+    fe_mul(j, h, i);
+    fe_sub(rr, s2, p.y); fe_dbl(rr, rr);
+    fe_mul(v, p.x, i);
+    fp_t x3, y3, z3;
+    fe_sqr(x3, rr); fe_sub(x3, x3, j); fe_dbl(t, v); fe_sub(x3, x3, t);
+    fe_sub(t, v, x3); fe_mul(t, rr, t);
+    fe_mul(s2, p.y, j); fe_dbl(s2, s2);
+    fe_sub(y3, t, s2);
+    fe_add(t, p.z, h); fe_sqr(t, t); fe_sub(t, t, z1z1); fe_sub(z3, t, hh);
+    r.x = x3; r.y = y3; r.z = z3;
+}
+KZG_HD void g1j_to_affine(g1_affine_t &r, const g1_jac_t &p) {
+    if (g1j_is_inf(p)) { g1a_set_inf(r); return; }
+    fp_t zi, zi2, zi3;
+    fp_inv(zi, p.z);
+    fe_sqr(zi2, zi);
+    fe_mul(zi3, zi2, zi);
+    fe_mul(r.x, p.x, zi2);
+    fe_mul(r.y, p.y, zi3);
+}
+// [k]P for a canonical little-endian scalar of `nbits` bits (double-and-add, P affine)
+KZG_HD void g1j_mul(g1_jac_t &r, const g1_affine_t &p, const uint32_t *k, int nbits) {
+    g1_jac_t acc;
+    g1j_set_inf(acc);
+    if (g1a_is_inf(p)) { r = acc; return; }
+#pragma unroll 1
+    for (int i = nbits - 1; i >= 0; i--) {
+        g1j_dbl(acc, acc);
+        if ((k[i >> 5] >> (i & 31)) & 1) g1j_add_affine(acc, acc, p.x, p.y);
+    }
+    r = acc;
+}
+
+// ------------------------------------------------------------------ serialisation
+// 48 big-endian bytes <-> 12 canonical limbs
+KZG_HD void fp_from_be48(fp_t &r, const uint8_t *b) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const uint8_t *q = b + 4 * (11 - i);
+        r.l[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+    }
+}
+KZG_HD void fp_to_be48(uint8_t *b, const fp_t &canon) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint8_t *q = b + 4 * (11 - i);
+        uint32_t v = canon.l[i];
+        q[0] = (uint8_t)(v >> 24); q[1] = (uint8_t)(v >> 16); q[2] = (uint8_t)(v >> 8); q[3] = (uint8_t)v;
+    }
+}
+// blst_p1_compress (reference src/utils.rs:221-227)
+KZG_HD void g1a_compress(uint8_t out[48], const g1_affine_t &p) {
+    if (g1a_is_inf(p)) {
+#pragma unroll
+        for (int i = 0; i < 48; i++) out[i] = 0;
+        out[0] = 0xC0;
+        return;
+    }
+    fp_t cx;
+    fe_from_mont(cx, p.x);
+    fp_to_be48(out, cx);
+    out[0] |= 0x80;
+    if (fp_is_lexicographically_largest(p.y)) out[0] |= 0x20;
+}
+// blst_p1_uncompress: false on any malformed encoding (bit 7 clear, bad infinity, x >= p,
+// x^3 + 4 not a square).  No subgroup check here.
+KZG_HD bool g1a_uncompress(g1_affine_t &out, const uint8_t in[48]) {
+    uint8_t b0 = in[0];
+    if (!(b0 & 0x80)) return false;
+    if (b0 & 0x40) {
+        uint32_t o = b0 & 0x3F;
+#pragma unroll 1
+        for (int i = 1; i < 48; i++) o |= in[i];
+        if (o) return false;
+        g1a_set_inf(out);
+        return true;
+    }
+    uint8_t tmp[48];
+#pragma unroll
+    for (int i = 0; i < 48; i++) tmp[i] = in[i];
+    tmp[0] &= 0x1F;
+    fp_t x;
+    fp_from_be48(x, tmp);
+    uint32_t m[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) m[i] = FpParams::mod(i);
+    if (limbs_geq<12>(x.l, m)) return false;
+    fe_to_mont(x, x);
+    fp_t rhs, y;
+    fe_sqr(rhs, x);
+    fe_mul(rhs, rhs, x);
+    fe_add(rhs, rhs, fp_const_b());
+    if (!fp_sqrt(y, rhs)) return false;
+    if (fp_is_lexicographically_largest(y) != ((b0 & 0x20) != 0)) fe_neg(y, y);
+    out.x = x;
+    out.y = y;
+    return true;
+}
+// blst_p1_in_g1 stand-in: P has order dividing r  <=>  [r]P == infinity
+KZG_HD bool g1a_in_subgroup(const g1_affine_t &p) {
+    uint32_t k[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) k[i] = FrParams::mod(i);
+    g1_jac_t t;
+    g1j_mul(t, p, k, 255);
+    return g1j_is_inf(t);
+}
+
+}  // namespace kzg

@@ -1,0 +1,473 @@
+// kzg_b200.cu -- kernels, context and C ABI of the B200 blob path (see include/kzg_b200.h).
+//
+// Host code here only sequences kernels and moves bytes; every arithmetic step of the
+// path runs on the GPU.  There is deliberately no CPU fallback: if CUDA is unusable the
+// entry points return KZG_B200_CUDA_ERROR.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/kzg_b200.h"
+#include "blobpath.cuh"
+#include "frpath.cuh"
+#include "host_pairing.h"
+#include "msm.cuh"
+
+using namespace kzg;
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            if (getenv("KZG_B200_DEBUG")) fprintf(stderr, "[kzg_b200] %s -> %s (%s:%d)\n", #expr, \
+                                                  cudaGetErrorString(e_), __FILE__, __LINE__);    \
+            return KZG_B200_CUDA_ERROR;                                                            \
+        }                                                                                          \
+    } while (0)
+#define RC(expr)                      \
+    do {                              \
+        int rc_ = (expr);             \
+        if (rc_ != KZG_B200_OK) return rc_; \
+    } while (0)
+
+// ------------------------------------------------------------------ context
+struct kzg_b200_ctx {
+    int device = 0;
+    int n = 0;        // FIELD_ELEMENTS_PER_BLOB
+    int c = 0;        // window bits
+    int W = 0;        // windows
+    uint32_t D = 0;   // table entries per (window, point): 2^(c-1)
+    int sms = 0;
+    int max_k = 512;  // additions per thread per inversion
+    g1_affine_t *d_table = nullptr;
+    fr_t *d_roots = nullptr;       // roots of unity, Montgomery form, bit-reversed (src/kzg.rs:764-799)
+    uint8_t g2_tau[96];            // [tau]G2 = g2_values[1]
+    // workspace for one chunk of blobs
+    size_t chunk = 0;
+    int16_t *d_digits = nullptr;
+    g1_affine_t *d_buf_a = nullptr, *d_buf_b = nullptr;
+    fp_t *d_scratch = nullptr;
+    size_t scratch_elems = 0;
+    uint8_t *d_stage_in = nullptr;    // chunk blobs
+    uint8_t *d_stage_aux = nullptr;   // chunk x 96 B (commitments / proofs / z)
+    uint8_t *d_stage_out = nullptr;   // chunk x 96 B
+    int32_t *d_status = nullptr;
+    fr_t *d_poly = nullptr;           // chunk x n (proof / verify paths)
+    fr_t *d_zy = nullptr;             // chunk x 2
+    g1_affine_t *d_pts = nullptr;     // chunk x 2 decoded commitments / proofs
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    std::mutex mu;
+};
+
+// ------------------------------------------------------------------ kernels
+__global__ void k_decode_g1(const uint8_t *in, g1_affine_t *out, int32_t *status, uint32_t count, int check_subgroup,
+                            int status_stride) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    g1_affine_t p;
+    int rc = g1_decode_thread(p, in + 48ull * i, check_subgroup != 0);
+    out[i] = p;
+    if (rc != KZG_OK && status) atomicMax(status + (size_t)i * status_stride, rc);
+}
+// table[i*D] = decoded[bitrev(i)]   (reference bit_reversal_permutation, src/kzg.rs:717-731)
+__global__ void k_place_bases(const g1_affine_t *decoded, g1_affine_t *table, uint32_t n, uint32_t D) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t r = 0, v = i;
+    for (uint32_t o = n; o > 1; o >>= 1) { r = (r << 1) | (v & 1); v >>= 1; }
+    table[(uint64_t)i * D] = decoded[r];
+}
+__global__ void k_window_bases(g1_affine_t *table, int n, int c, int W, uint32_t D) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint32_t)n) return;
+    window_base_thread(table, i, n, c, W, D);
+}
+__global__ void k_blob_digits(const uint8_t *blobs, uint64_t total, int n, int c, int W, int16_t *digits,
+                              int32_t *status) {
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    blob_digits_thread(blobs, e, n, c, W, digits, status);
+}
+__global__ void k_fr_digits(const fr_t *evals, uint64_t total, int n, int c, int W, int16_t *digits) {
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    fr_digits_thread(evals, e, n, c, W, digits);
+}
+__global__ void k_compress(const g1_affine_t *pts, const int32_t *status, uint8_t *out, uint32_t count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint8_t buf[48];
+    if (status && status[i] != KZG_OK) {
+        for (int k = 0; k < 48; k++) buf[k] = 0;
+    } else {
+        g1a_compress(buf, pts[i]);
+    }
+    uint32_t *o = reinterpret_cast<uint32_t *>(out + 48ull * i);
+#pragma unroll
+    for (int k = 0; k < 12; k++)
+        o[k] = (uint32_t)buf[4 * k] | ((uint32_t)buf[4 * k + 1] << 8) | ((uint32_t)buf[4 * k + 2] << 16) | ((uint32_t)buf[4 * k + 3] << 24);
+}
+__global__ void k_fill_i32(int32_t *p, int32_t v, uint64_t count) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) p[i] = v;
+}
+
+// ---- micro-benchmarks for the roofline denominators
+__global__ void k_peak_imad(uint32_t *out, int iters) {
+    uint32_t a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 3;
+    uint32_t x0 = a, x1 = a + 1, x2 = a + 2, x3 = a + 3, x4 = a + 4, x5 = a + 5, x6 = a + 6, x7 = a + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            asm volatile("mad.lo.u32 %0, %0, %8, %9;\n\tmad.lo.u32 %1, %1, %8, %9;\n\tmad.lo.u32 %2, %2, %8, %9;\n\t"
+                         "mad.lo.u32 %3, %3, %8, %9;\n\tmad.lo.u32 %4, %4, %8, %9;\n\tmad.lo.u32 %5, %5, %8, %9;\n\t"
+                         "mad.lo.u32 %6, %6, %8, %9;\n\tmad.lo.u32 %7, %7, %8, %9;"
+                         : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7)
+                         : "r"(b), "r"(a));
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+}
+__global__ void __launch_bounds__(KZG_ADD_THREADS, KZG_ADD_MIN_BLOCKS) k_peak_fpmul(fp_t *out, int iters) {
+    fp_t x = fe_one<FpParams>(), y = fp_const_b();
+    x.l[0] += threadIdx.x;
+    y.l[1] ^= blockIdx.x;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+        fe_mul(x, x, y);
+        fe_mul(y, y, x);
+    }
+    fe_add(x, x, y);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+// ------------------------------------------------------------------ launch helpers
+static inline unsigned blocks_for(uint64_t total, unsigned tpb) { return (unsigned)((total + tpb - 1) / tpb); }
+
+static int ensure_scratch(kzg_b200_ctx *ctx, size_t elems) {
+    if (elems <= ctx->scratch_elems) return KZG_B200_OK;
+    if (ctx->d_scratch) CU(cudaFree(ctx->d_scratch));
+    ctx->d_scratch = nullptr;
+    ctx->scratch_elems = 0;
+    CU(cudaMalloc(&ctx->d_scratch, elems * sizeof(fp_t)));
+    ctx->scratch_elems = elems;
+    return KZG_B200_OK;
+}
+
+template <class Policy>
+static int launch_batch_add(kzg_b200_ctx *ctx, const Policy &pol, uint64_t total) {
+    if (total == 0) return KZG_B200_OK;
+    const unsigned tpb = KZG_ADD_THREADS;
+    const uint64_t t_max = (uint64_t)ctx->sms * KZG_ADD_MIN_BLOCKS * tpb;
+    uint64_t T;
+    int k;
+    if (total <= t_max) {
+        T = (total + tpb - 1) / tpb * tpb;
+        k = 1;
+    } else {
+        T = t_max;
+        uint64_t need = (total + T - 1) / T;
+        k = (int)std::min<uint64_t>(need, (uint64_t)ctx->max_k);
+    }
+    RC(ensure_scratch(ctx, (size_t)(T * k)));
+    batch_add_kernel<Policy><<<(unsigned)(T / tpb), tpb, 0, ctx->stream>>>(pol, total, ctx->d_scratch, k);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return KZG_B200_OK;
+}
+
+// sum of the W*n table entries selected by d_digits, for `count` blobs -> result[b] in *out
+static int run_msm(kzg_b200_ctx *ctx, size_t count, const g1_affine_t **out) {
+    uint32_t per_blob = (uint32_t)ctx->W * ctx->n, cnt = per_blob / 2;
+    GatherPolicy gp{ctx->d_table, ctx->d_digits, ctx->d_buf_a, per_blob, ctx->D};
+    RC(launch_batch_add(ctx, gp, (uint64_t)count * cnt));
+    g1_affine_t *in = ctx->d_buf_a, *o = ctx->d_buf_b;
+    while (cnt > 1) {
+        uint32_t nxt = (cnt + 1) / 2;
+        TreePolicy tp{in, o, cnt, nxt};
+        RC(launch_batch_add(ctx, tp, (uint64_t)count * nxt));
+        std::swap(in, o);
+        cnt = nxt;
+    }
+    *out = in;
+    return KZG_B200_OK;
+}
+
+// ------------------------------------------------------------------ workspace
+static size_t per_blob_workspace(const kzg_b200_ctx *ctx) {
+    size_t wn = (size_t)ctx->W * ctx->n;
+    return wn * 2 /*digits*/ + wn / 2 * sizeof(g1_affine_t) + (wn / 4 + 1) * sizeof(g1_affine_t) +
+           (size_t)ctx->n * 32 /*stage in*/ + (size_t)ctx->n * sizeof(fr_t) /*poly*/ + 96 * 2 + 2 * sizeof(fr_t) +
+           2 * sizeof(g1_affine_t) + 4;
+}
+static void free_workspace(kzg_b200_ctx *ctx) {
+    cudaFree(ctx->d_digits); cudaFree(ctx->d_buf_a); cudaFree(ctx->d_buf_b); cudaFree(ctx->d_stage_in);
+    cudaFree(ctx->d_stage_aux); cudaFree(ctx->d_stage_out); cudaFree(ctx->d_status); cudaFree(ctx->d_poly);
+    cudaFree(ctx->d_zy); cudaFree(ctx->d_pts);
+    ctx->d_digits = nullptr; ctx->d_buf_a = ctx->d_buf_b = nullptr; ctx->d_stage_in = ctx->d_stage_aux = ctx->d_stage_out = nullptr;
+    ctx->d_status = nullptr; ctx->d_poly = nullptr; ctx->d_zy = nullptr; ctx->d_pts = nullptr;
+    ctx->chunk = 0;
+}
+static int alloc_workspace(kzg_b200_ctx *ctx, size_t chunk) {
+    free_workspace(ctx);
+    size_t wn = (size_t)ctx->W * ctx->n;
+    CU(cudaMalloc(&ctx->d_digits, chunk * wn * sizeof(int16_t)));
+    CU(cudaMalloc(&ctx->d_buf_a, chunk * (wn / 2) * sizeof(g1_affine_t)));
+    CU(cudaMalloc(&ctx->d_buf_b, chunk * (wn / 4 + 1) * sizeof(g1_affine_t)));
+    CU(cudaMalloc(&ctx->d_stage_in, chunk * (size_t)ctx->n * 32));
+    CU(cudaMalloc(&ctx->d_stage_aux, chunk * 96));
+    CU(cudaMalloc(&ctx->d_stage_out, chunk * 96));
+    CU(cudaMalloc(&ctx->d_status, chunk * sizeof(int32_t)));
+    CU(cudaMalloc(&ctx->d_poly, chunk * (size_t)ctx->n * sizeof(fr_t)));
+    CU(cudaMalloc(&ctx->d_zy, chunk * 2 * sizeof(fr_t)));
+    CU(cudaMalloc(&ctx->d_pts, chunk * 2 * sizeof(g1_affine_t)));
+    ctx->chunk = chunk;
+    return KZG_B200_OK;
+}
+
+// ------------------------------------------------------------------ context creation
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+static int build_table(kzg_b200_ctx *ctx, const uint8_t *g1_bytes) {
+    const int n = ctx->n;
+    uint8_t *d_bytes = nullptr;
+    g1_affine_t *d_dec = nullptr;
+    int32_t *d_st = nullptr;
+    CU(cudaMalloc(&d_bytes, (size_t)n * 48));
+    CU(cudaMalloc(&d_dec, (size_t)n * sizeof(g1_affine_t)));
+    CU(cudaMalloc(&d_st, (size_t)n * sizeof(int32_t)));
+    CU(cudaMemcpyAsync(d_bytes, g1_bytes, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(d_st, 0, (size_t)n * sizeof(int32_t), ctx->stream));
+    // reference load_trusted_setup does not subgroup-check the G1 points (src/kzg.rs:859-872)
+    k_decode_g1<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(d_bytes, d_dec, d_st, n, 0, 1);
+    ctx->launches++;
+    std::vector<int32_t> st(n);
+    CU(cudaMemcpyAsync(st.data(), d_st, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; i++)
+        if (st[i] != 0) { cudaFree(d_bytes); cudaFree(d_dec); cudaFree(d_st); return KZG_B200_BAD_ARGS; }
+    k_place_bases<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(d_dec, ctx->d_table, n, ctx->D);
+    k_window_bases<<<blocks_for(n, 32), 32, 0, ctx->stream>>>(ctx->d_table, n, ctx->c, ctx->W, ctx->D);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    for (int L = 0; L + 1 < ctx->c; L++) {
+        TableLevelPolicy pol{ctx->d_table, ctx->D, (uint32_t)L};
+        RC(launch_batch_add(ctx, pol, ((uint64_t)ctx->W * n) << L));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_bytes); cudaFree(d_dec); cudaFree(d_st);
+    return KZG_B200_OK;
+}
+
+extern "C" int kzg_b200_ctx_create(const uint8_t *g1_lagrange, size_t n1, const uint8_t *g2_monomial, size_t n2,
+                                   int device, int window_bits, kzg_b200_ctx **out) {
+    if (!g1_lagrange || !g2_monomial || !out) return KZG_B200_BAD_ARGS;
+    // reference src/kzg.rs:843-847 (n1 fixed per preset; both presets accepted here)
+    if ((n1 != 4096 && n1 != 4) || n2 != KZG_B200_NUM_G2_POINTS) return KZG_B200_BAD_ARGS;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return KZG_B200_CUDA_ERROR;
+    CU(cudaSetDevice(device));
+    // G2 side of the setup on the host: decode all 65 points (reference src/kzg.rs:874-887) and
+    // run the Lagrange-form sanity pairing (src/kzg.rs:802-830) -- it needs g1[0], g1[1] only.
+    {
+        int rc = host_check_setup(g1_lagrange, g2_monomial, n2);
+        if (rc != KZG_B200_OK) return rc;
+    }
+    kzg_b200_ctx *ctx = new kzg_b200_ctx();
+    ctx->device = device;
+    ctx->n = (int)n1;
+    memcpy(ctx->g2_tau, g2_monomial + 96, 96);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return KZG_B200_CUDA_ERROR; }
+    ctx->sms = prop.multiProcessorCount;
+    ctx->max_k = env_int("KZG_B200_BATCH_K", 512);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KZG_B200_CUDA_ERROR; }
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    int c = window_bits > 0 ? window_bits : env_int("KZG_B200_WINDOW_BITS", 0);
+    if (c <= 0) {
+        // largest window whose table leaves room for a 4096-blob workspace and 16 GiB of caller data
+        for (c = 15; c > 2; c--) {
+            size_t tbl = (size_t)msm_num_windows(c) * n1 * ((size_t)1 << (c - 1)) * sizeof(g1_affine_t);
+            if (tbl + ((size_t)40 << 30) <= free_b) break;
+        }
+    }
+    if (c < 2 || c > 15) { kzg_b200_ctx_destroy(ctx); return KZG_B200_BAD_ARGS; }
+    ctx->c = c;
+    ctx->W = msm_num_windows(c);
+    ctx->D = 1u << (c - 1);
+    size_t tbl_bytes = (size_t)ctx->W * n1 * ctx->D * sizeof(g1_affine_t);
+    if (cudaMalloc(&ctx->d_table, tbl_bytes) != cudaSuccess) { kzg_b200_ctx_destroy(ctx); return KZG_B200_CUDA_ERROR; }
+    int rc = build_table(ctx, g1_lagrange);
+    if (rc != KZG_B200_OK) { kzg_b200_ctx_destroy(ctx); return rc; }
+    rc = fr_setup_roots(ctx->n, &ctx->d_roots, ctx->stream);
+    if (rc != KZG_B200_OK) { kzg_b200_ctx_destroy(ctx); return rc; }
+    // workspace: as many blobs per chunk as memory allows, capped (KZG_B200_CHUNK overrides)
+    cudaMemGetInfo(&free_b, &total_b);
+    size_t cap = (size_t)env_int("KZG_B200_CHUNK", 4096);
+    size_t reserve = (size_t)12 << 30;  // leave room for the caller's device-resident blobs
+    size_t usable = free_b > reserve + ((size_t)2 << 30) ? free_b - reserve : free_b / 2;
+    size_t chunk = std::max<size_t>(1, std::min(cap, usable / per_blob_workspace(ctx)));
+    rc = alloc_workspace(ctx, chunk);
+    if (rc != KZG_B200_OK) { kzg_b200_ctx_destroy(ctx); return rc; }
+    *out = ctx;
+    return KZG_B200_OK;
+}
+
+static int hex_nibble(int ch) {
+    if (ch >= '0' && ch <= '9') return ch - '0';
+    if (ch >= 'a' && ch <= 'f') return ch - 'a' + 10;
+    if (ch >= 'A' && ch <= 'F') return ch - 'A' + 10;
+    return -1;
+}
+// reference load_trusted_setup_file, src/kzg.rs:906-979
+extern "C" int kzg_b200_ctx_create_from_file(const char *path, int device, int window_bits, kzg_b200_ctx **out) {
+    FILE *f = fopen(path, "r");
+    if (!f) return KZG_B200_INVALID_TRUSTED_SETUP;
+    unsigned long n1 = 0, n2 = 0;
+    if (fscanf(f, "%lu", &n1) != 1 || fscanf(f, "%lu", &n2) != 1 || (n1 != 4096 && n1 != 4) || n2 != 65) {
+        fclose(f);
+        return KZG_B200_INVALID_TRUSTED_SETUP;
+    }
+    std::vector<uint8_t> g1(n1 * 48), g2(n2 * 96);
+    char tok[512];
+    int rc = KZG_B200_OK;
+    for (size_t i = 0; i < n1 + n2 && rc == KZG_B200_OK; i++) {
+        size_t want = i < n1 ? 48 : 96;
+        uint8_t *dst = i < n1 ? g1.data() + 48 * i : g2.data() + 96 * (i - n1);
+        if (fscanf(f, "%511s", tok) != 1) { rc = KZG_B200_INVALID_TRUSTED_SETUP; break; }
+        const char *h = tok;
+        if (h[0] == '0' && h[1] == 'x') h += 2;
+        if (strlen(h) != 2 * want) { rc = KZG_B200_INVALID_HEX_FORMAT; break; }
+        for (size_t k = 0; k < want; k++) {
+            int hi = hex_nibble(h[2 * k]), lo = hex_nibble(h[2 * k + 1]);
+            if (hi < 0 || lo < 0) { rc = KZG_B200_INVALID_HEX_FORMAT; break; }
+            dst[k] = (uint8_t)(hi << 4 | lo);
+        }
+    }
+    fclose(f);
+    if (rc != KZG_B200_OK) return rc;
+    return kzg_b200_ctx_create(g1.data(), n1, g2.data(), n2, device, window_bits, out);
+}
+
+extern "C" void kzg_b200_ctx_destroy(kzg_b200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_workspace(ctx);
+    cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_table);
+    cudaFree(ctx->d_roots);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" size_t kzg_b200_field_elements_per_blob(const kzg_b200_ctx *ctx) { return ctx ? (size_t)ctx->n : 0; }
+extern "C" int kzg_b200_window_bits(const kzg_b200_ctx *ctx) { return ctx ? ctx->c : 0; }
+extern "C" void *kzg_b200_stream(kzg_b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" uint64_t kzg_b200_launch_count(const kzg_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int kzg_b200_synchronize(kzg_b200_ctx *ctx) {
+    if (!ctx) return KZG_B200_BAD_ARGS;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KZG_B200_OK;
+}
+
+// ------------------------------------------------------------------ blob_to_kzg_commitment
+// one chunk, everything on the device: blobs -> digits -> MSM -> 48-byte commitments
+static int commit_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, size_t count, uint8_t *d_out, int32_t *d_status) {
+    const uint64_t elems = (uint64_t)count * ctx->n;
+    CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), ctx->stream));
+    k_blob_digits<<<blocks_for(elems, 256), 256, 0, ctx->stream>>>(d_blobs, elems, ctx->n, ctx->c, ctx->W, ctx->d_digits, d_status);
+    ctx->launches++;
+    const g1_affine_t *res = nullptr;
+    RC(run_msm(ctx, count, &res));
+    k_compress<<<blocks_for(count, 64), 64, 0, ctx->stream>>>(res, d_status, d_out, (uint32_t)count);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return KZG_B200_OK;
+}
+
+extern "C" int kzg_b200_blob_to_kzg_commitment_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, size_t n, uint8_t *d_out,
+                                                      int32_t *d_status) {
+    if (!ctx || (n && (!d_blobs || !d_out || !d_status))) return KZG_B200_BAD_ARGS;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const size_t bpb = (size_t)ctx->n * 32;
+    for (size_t off = 0; off < n; off += ctx->chunk) {
+        size_t cnt = std::min(ctx->chunk, n - off);
+        RC(commit_chunk(ctx, d_blobs + off * bpb, cnt, d_out + off * 48, d_status + off));
+    }
+    return KZG_B200_OK;
+}
+
+extern "C" int kzg_b200_blob_to_kzg_commitment_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, size_t n, uint8_t *out,
+                                                     int32_t *status) {
+    if (!ctx || (n && (!blobs || !out || !status))) return KZG_B200_BAD_ARGS;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const size_t bpb = (size_t)ctx->n * 32;
+    for (size_t off = 0; off < n; off += ctx->chunk) {
+        size_t cnt = std::min(ctx->chunk, n - off);
+        CU(cudaMemcpyAsync(ctx->d_stage_in, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->stream));
+        RC(commit_chunk(ctx, ctx->d_stage_in, cnt, ctx->d_stage_out, ctx->d_status));
+        CU(cudaMemcpyAsync(out + off * 48, ctx->d_stage_out, cnt * 48, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(status + off, ctx->d_status, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return KZG_B200_OK;
+}
+
+// ------------------------------------------------------------------ roofline micro-benchmarks
+extern "C" int kzg_b200_measure_peaks(kzg_b200_ctx *ctx, double *imad_per_s, double *fp_mul_per_s) {
+    if (!ctx) return KZG_B200_BAD_ARGS;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float ms = 0;
+    {
+        const int blocks = ctx->sms * 8, tpb = 256, iters = 4096;
+        uint32_t *d = nullptr;
+        CU(cudaMalloc(&d, (size_t)blocks * tpb * 4));
+        k_peak_imad<<<blocks, tpb, 0, ctx->stream>>>(d, 64);
+        CU(cudaEventRecord(e0, ctx->stream));
+        k_peak_imad<<<blocks, tpb, 0, ctx->stream>>>(d, iters);
+        CU(cudaEventRecord(e1, ctx->stream));
+        CU(cudaEventSynchronize(e1));
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (imad_per_s) *imad_per_s = (double)blocks * tpb * iters * 64.0 / (ms * 1e-3);
+        cudaFree(d);
+    }
+    {
+        const int blocks = ctx->sms * KZG_ADD_MIN_BLOCKS, tpb = KZG_ADD_THREADS, iters = 2048;
+        fp_t *d = nullptr;
+        CU(cudaMalloc(&d, (size_t)blocks * tpb * sizeof(fp_t)));
+        k_peak_fpmul<<<blocks, tpb, 0, ctx->stream>>>(d, 16);
+        CU(cudaEventRecord(e0, ctx->stream));
+        k_peak_fpmul<<<blocks, tpb, 0, ctx->stream>>>(d, iters);
+        CU(cudaEventRecord(e1, ctx->stream));
+        CU(cudaEventSynchronize(e1));
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (fp_mul_per_s) *fp_mul_per_s = (double)blocks * tpb * iters * 2.0 / (ms * 1e-3);
+        cudaFree(d);
+    }
+    ctx->launches += 4;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return KZG_B200_OK;
+}
+
+#include "proof_verify.inl"

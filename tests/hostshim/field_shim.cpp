@@ -1,0 +1,17 @@
+// Host-side shim exposing the product's field templates (host code path of
+// kzg_rust_b200/csrc/bigint.cuh) to ctypes, so tests can compare them with Python ints.
+#include "../../kzg_rust_b200/csrc/fields.cuh"
+using namespace kzg;
+extern "C" {
+void shim_fp_mul(const uint32_t *a, const uint32_t *b, uint32_t *r) { fp_t x, y, z; memcpy(x.l, a, 48); memcpy(y.l, b, 48); fe_mul(z, x, y); memcpy(r, z.l, 48); }
+void shim_fp_add(const uint32_t *a, const uint32_t *b, uint32_t *r) { fp_t x, y, z; memcpy(x.l, a, 48); memcpy(y.l, b, 48); fe_add(z, x, y); memcpy(r, z.l, 48); }
+void shim_fp_sub(const uint32_t *a, const uint32_t *b, uint32_t *r) { fp_t x, y, z; memcpy(x.l, a, 48); memcpy(y.l, b, 48); fe_sub(z, x, y); memcpy(r, z.l, 48); }
+void shim_fp_inv(const uint32_t *a, uint32_t *r) { fp_t x, z; memcpy(x.l, a, 48); fp_inv(z, x); memcpy(r, z.l, 48); }
+int shim_fp_sqrt(const uint32_t *a, uint32_t *r) { fp_t x, z; memcpy(x.l, a, 48); bool ok = fp_sqrt(z, x); memcpy(r, z.l, 48); return ok; }
+int shim_fp_large(const uint32_t *a) { fp_t x; memcpy(x.l, a, 48); return fp_is_lexicographically_largest(x); }
+void shim_fr_mul(const uint32_t *a, const uint32_t *b, uint32_t *r) { fr_t x, y, z; memcpy(x.l, a, 32); memcpy(y.l, b, 32); fe_mul(z, x, y); memcpy(r, z.l, 32); }
+void shim_fr_add(const uint32_t *a, const uint32_t *b, uint32_t *r) { fr_t x, y, z; memcpy(x.l, a, 32); memcpy(y.l, b, 32); fe_add(z, x, y); memcpy(r, z.l, 32); }
+void shim_fr_sub(const uint32_t *a, const uint32_t *b, uint32_t *r) { fr_t x, y, z; memcpy(x.l, a, 32); memcpy(y.l, b, 32); fe_sub(z, x, y); memcpy(r, z.l, 32); }
+void shim_fr_inv(const uint32_t *a, uint32_t *r) { fr_t x, z; memcpy(x.l, a, 32); fr_inv(z, x); memcpy(r, z.l, 32); }
+int shim_fr_canonical(const uint32_t *a) { fr_t x; memcpy(x.l, a, 32); return fr_is_canonical(x); }
+}

@@ -1,0 +1,49 @@
+// CPU walk-through of the product's commitment pipeline (host code path of the same
+// headers the CUDA kernels are built from): decode setup -> bit-reverse -> window bases
+// -> table levels -> digits -> gather level -> tree levels -> compress.  "Threads" are
+// iterated sequentially.  Small presets only (n = 4); used by tests/test_host_logic.py.
+#include <vector>
+#include "../../kzg_rust_b200/csrc/msm.cuh"
+#include "../../kzg_rust_b200/csrc/blobpath.cuh"
+using namespace kzg;
+
+template <class Policy>
+static void run_level(const Policy &pol, uint64_t total, int T, int k) {
+    std::vector<fp_t> scratch((size_t)T * k);
+    for (int tid = 0; tid < T; tid++) batch_add_thread(pol, total, scratch.data(), k, (uint64_t)T, (uint64_t)tid);
+}
+static uint32_t bitrev(uint32_t v, int n) { uint32_t r = 0; for (int o = n; o > 1; o >>= 1) { r = (r << 1) | (v & 1); v >>= 1; } return r; }
+
+extern "C" int shim_commit(const uint8_t *g1_bytes, int n, int c, const uint8_t *blobs, int B, uint8_t *out,
+                           int *status, int T, int k) {
+    const int W = msm_num_windows(c);
+    const uint32_t D = 1u << (c - 1);
+    std::vector<g1_affine_t> table((size_t)W * n * D);
+    for (int i = 0; i < n; i++) {
+        g1_affine_t p;
+        if (g1_decode_thread(p, g1_bytes + 48 * bitrev(i, n), false)) return KZG_BADARGS;
+        table[(size_t)i * D] = p;
+    }
+    for (int i = 0; i < n; i++) window_base_thread(table.data(), i, n, c, W, D);
+    for (int L = 0; L + 1 < c; L++) {
+        TableLevelPolicy pol{table.data(), D, (uint32_t)L};
+        run_level(pol, (uint64_t)W * n << L, T, k);
+    }
+    std::vector<int16_t> digits((size_t)B * W * n);
+    for (int b = 0; b < B; b++) status[b] = 0;
+    for (uint64_t e = 0; e < (uint64_t)B * n; e++) blob_digits_thread(blobs, e, n, c, W, digits.data(), status);
+    uint32_t per_blob = W * n, cnt = per_blob / 2;
+    std::vector<g1_affine_t> a((size_t)B * cnt), b2((size_t)B * cnt);
+    GatherPolicy gp{table.data(), digits.data(), a.data(), per_blob, D};
+    run_level(gp, (uint64_t)B * cnt, T, k);
+    g1_affine_t *in = a.data(), *o = b2.data();
+    while (cnt > 1) {
+        uint32_t nxt = (cnt + 1) / 2;
+        TreePolicy tp{in, o, cnt, nxt};
+        run_level(tp, (uint64_t)B * nxt, T, k);
+        std::swap(in, o);
+        cnt = nxt;
+    }
+    for (int b = 0; b < B; b++) g1a_compress(out + 48 * b, in[b]);
+    return 0;
+}
