@@ -151,9 +151,10 @@ int kzg_b200_pairings_verify(const uint8_t a1[48], const uint8_t a2[96], const u
                              const uint8_t b2[96], int *ok);
 
 /* Micro-benchmarks used by bench.py to measure the integer-multiply roofline on the device
- * the context is bound to: issue rate of independent 32-bit IMADs (ops/s) and of full Fp
- * Montgomery multiplications (mul/s).  */
-int kzg_b200_measure_peaks(kzg_b200_ctx *ctx, double *imad_per_s, double *fp_mul_per_s);
+ * the context is bound to: issue rate of independent 32-bit multiply-adds (mad.lo.u32 ->
+ * IMAD, ops/s), of independent 32x32+64 multiply-adds (mad.wide.u32 -> IMAD.WIDE, ops/s)
+ * and of dependent full Fp Montgomery multiplications (mul/s).  */
+int kzg_b200_measure_peaks(kzg_b200_ctx *ctx, double *imad_per_s, double *imad_wide_per_s, double *fp_mul_per_s);
 
 #ifdef __cplusplus
 }

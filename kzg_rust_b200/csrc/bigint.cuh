@@ -55,19 +55,37 @@ KZG_HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c, uint32_t &cc) { u
 KZG_HD uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
 #endif
 
-// acc[0 .. 2L] += sum_{k<L} x[2k] * m * 2^(64k).  One carry chain; the carry out of the
-// top pair lands in acc[2L] when CARRY_OUT (the callers know when it is provably zero).
-template <int L, bool CARRY_OUT>
-KZG_HD void mad_row(uint32_t *acc, const uint32_t *x, uint32_t m) {
-    uint32_t cc = 0;
+KZG_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c, uint32_t &cc) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+#else
+    return (uint32_t)((((uint64_t)a * b) >> 32) + c + cc);
+#endif
+}
+KZG_HD uint32_t mul_hi(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+// 64-bit columns.  x is read with stride 2 (x[0], x[2], ...): pass `a` for the even limbs
+// of an operand and `a + 1` for the odd ones.  N = limbs of the accumulator (even).
+//   mul_row : acc[2k+1:2k]  = x[2k] * m
+//   cmad_row: acc[2k+1:2k] += x[2k] * m  in one carry chain; the carry out is left in the flag
+template <int N> KZG_HD void mul_row(uint32_t *acc, const uint32_t *x, uint32_t m) {
+#pragma unroll
+    for (int k = 0; k < N; k += 2) { acc[k] = mul_lo(x[k], m); acc[k + 1] = mul_hi(x[k], m); }
+}
+template <int N> KZG_HD void cmad_row(uint32_t *acc, const uint32_t *x, uint32_t m, uint32_t &cc) {
     acc[0] = mad_lo_cc(x[0], m, acc[0], cc);
     acc[1] = madc_hi_cc(x[0], m, acc[1], cc);
 #pragma unroll
-    for (int k = 1; k < L; k++) {
-        acc[2 * k] = madc_lo_cc(x[2 * k], m, acc[2 * k], cc);
-        acc[2 * k + 1] = madc_hi_cc(x[2 * k], m, acc[2 * k + 1], cc);
+    for (int k = 2; k < N; k += 2) {
+        acc[k] = madc_lo_cc(x[k], m, acc[k], cc);
+        acc[k + 1] = madc_hi_cc(x[k], m, acc[k + 1], cc);
     }
-    if (CARRY_OUT) acc[2 * L] = addc(acc[2 * L], 0, cc);
 }
 
 // ------------------------------------------------------------------ the field template
@@ -141,64 +159,61 @@ template <class P> KZG_HD void fe_neg(Fe<P> &r, const Fe<P> &a) {
 }
 template <class P> KZG_HD void fe_dbl(Fe<P> &r, const Fe<P> &a) { fe_add(r, a, a); }
 
-// Montgomery product: separated operand scanning into even/odd accumulators, then an
-// interleaved-carry reduction.  Inputs < mod, output < mod.
+// Montgomery product, operand scanning with the reduction interleaved (CIOS), arranged for
+// the 64-bit multiply-add of the hardware (IMAD.WIDE): the running value is kept as
+//     V = E + 2^32 * O,     E = sum ev[k] 2^(32k),  O = sum od[k] 2^(32k)      (N limbs each)
+// so that x[even]*m lands on E's 64-bit columns and x[odd]*m on O's.  Each step adds
+// a*b_i and m*mod (m chosen so that V becomes divisible by 2^32) and divides by 2^32:
+// O becomes the new E, E >> 64 the new O, and the stray limb E[1] is added at the bottom
+// of the new E with its carry entering the new O's chain.
+// Bounds (mod < 2^(32N-2)): V < 2 mod before a step and < 2 mod 2^32 inside it, hence
+// O < 2^(32N) always -- no chain on O ever carries out; a chain on E may, and that carry
+// (weight 2^(32N)) is added to O's top limb.  Inputs < mod, output < mod.
 template <class P> KZG_HD void fe_mul(Fe<P> &r, const Fe<P> &a, const Fe<P> &b) {
-    constexpr int N = P::N, H = P::N / 2;
-    // value = sum ev[k] 2^(32k) + sum od[k] 2^(32(k+1))
-    uint32_t ev[2 * N + 2], od[2 * N + 2];
-#pragma unroll
-    for (int i = 0; i < 2 * N + 2; i++) { ev[i] = 0; od[i] = 0; }
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        if ((i & 1) == 0) {
-            mad_row<H, true>(ev + i, a.l, b.l[i]);
-            mad_row<H, true>(od + i, a.l + 1, b.l[i]);
-        } else {
-            mad_row<H, true>(od + i - 1, a.l, b.l[i]);
-            mad_row<H, (true)>(ev + i + 1, a.l + 1, b.l[i]);
-        }
-    }
+    constexpr int N = P::N;
     uint32_t mp[N];
 #pragma unroll
     for (int i = 0; i < N; i++) mp[i] = P::mod(i);
-    uint32_t carry = 0;
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        uint32_t t = ev[i] + (i > 0 ? od[i - 1] : 0u) + carry;
-        uint32_t m = mul_lo(t, P::n0);
-        if ((i & 1) == 0) {
-            mad_row<H, true>(ev + i, mp, m);
-            mad_row<H, true>(od + i, mp + 1, m);
-        } else {
-            mad_row<H, true>(od + i - 1, mp, m);
-            mad_row<H, true>(ev + i + 1, mp + 1, m);
-        }
-        // limb i is now 0 mod 2^32; what is left of it is a carry of 0, 1 or 2
-        uint32_t cc = 0, c1, c2;
-        uint32_t s = add_cc(ev[i], (i > 0 ? od[i - 1] : 0u), cc);
-        c1 = addc(0, 0, cc);
-        (void)add_cc(s, carry, cc);
-        c2 = addc(0, 0, cc);
-        carry = c1 + c2;
-    }
-    Fe<P> t;
+    uint32_t x[N], y[N];  // x plays E and y plays O in even steps; swapped in odd steps
     uint32_t cc = 0;
+    // step 0
+    mul_row<N>(x, a.l, b.l[0]);
+    mul_row<N>(y, a.l + 1, b.l[0]);
     {
-        uint32_t s = add_cc(ev[N], od[N - 1], cc);
-        uint32_t c1 = addc(0, 0, cc);
-        t.l[0] = add_cc(s, carry, cc);
-        uint32_t c2 = addc(0, 0, cc);
-        carry = c1 + c2;
+        uint32_t m = mul_lo(x[0], P::n0);
+        cmad_row<N>(y, mp + 1, m, cc);
+        cmad_row<N>(x, mp, m, cc);
+        y[N - 1] = addc(y[N - 1], 0, cc);
     }
 #pragma unroll
-    for (int k = 1; k < N; k++) {
-        uint32_t s = add_cc(ev[N + k], od[N + k - 1], cc);
-        uint32_t c1 = addc(0, 0, cc);
-        t.l[k] = add_cc(s, carry, cc);
-        uint32_t c2 = addc(0, 0, cc);
-        carry = c1 + c2;
+    for (int i = 1; i < N; i++) {
+        uint32_t *E = (i & 1) ? y : x;  // the accumulator that is E during this step
+        uint32_t *O = (i & 1) ? x : y;  // old E, becomes O after the shift by 64 bits
+        const uint32_t bi = b.l[i];
+        E[0] = add_cc(E[0], O[1], cc);
+        // O = (O >> 64) + a_odd * b_i + carry
+#pragma unroll
+        for (int k = 0; k < N - 2; k += 2) {
+            O[k] = madc_lo_cc(a.l[k + 1], bi, O[k + 2], cc);
+            O[k + 1] = madc_hi_cc(a.l[k + 1], bi, O[k + 3], cc);
+        }
+        O[N - 2] = madc_lo_cc(a.l[N - 1], bi, 0, cc);
+        O[N - 1] = madc_hi(a.l[N - 1], bi, 0, cc);
+        cmad_row<N>(E, a.l, bi, cc);
+        O[N - 1] = addc(O[N - 1], 0, cc);
+        uint32_t m = mul_lo(E[0], P::n0);
+        cmad_row<N>(O, mp + 1, m, cc);
+        cmad_row<N>(E, mp, m, cc);
+        O[N - 1] = addc(O[N - 1], 0, cc);
     }
+    // result = O + (E >> 32), E[0] == 0.  After step N-1 (odd): E = y, O = x.
+    uint32_t *E = ((N - 1) & 1) ? y : x;
+    uint32_t *O = ((N - 1) & 1) ? x : y;
+    Fe<P> t;
+    t.l[0] = add_cc(O[0], E[1], cc);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) t.l[k] = addc_cc(O[k], E[k + 1], cc);
+    t.l[N - 1] = addc(O[N - 1], 0, cc);
     fe_reduce_once(t, 0);
     r = t;
 }

@@ -136,6 +136,22 @@ __global__ void k_peak_imad(uint32_t *out, int iters) {
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
 }
+__global__ void k_peak_imad_wide(uint64_t *out, int iters) {
+    uint32_t a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 3;
+    uint64_t x0 = a, x1 = a + 1, x2 = a + 2, x3 = a + 3, x4 = a + 4, x5 = a + 5, x6 = a + 6, x7 = a + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\tmad.wide.u32 %2, %8, %9, %2;\n\t"
+                         "mad.wide.u32 %3, %8, %9, %3;\n\tmad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\t"
+                         "mad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
+                         : "+l"(x0), "+l"(x1), "+l"(x2), "+l"(x3), "+l"(x4), "+l"(x5), "+l"(x6), "+l"(x7)
+                         : "r"(b), "r"(a));
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+}
 __global__ void __launch_bounds__(KZG_ADD_THREADS, KZG_ADD_MIN_BLOCKS) k_peak_fpmul(fp_t *out, int iters) {
     fp_t x = fe_one<FpParams>(), y = fp_const_b();
     x.l[0] += threadIdx.x;
@@ -430,7 +446,8 @@ extern "C" int kzg_b200_blob_to_kzg_commitment_batch(kzg_b200_ctx *ctx, const ui
 }
 
 // ------------------------------------------------------------------ roofline micro-benchmarks
-extern "C" int kzg_b200_measure_peaks(kzg_b200_ctx *ctx, double *imad_per_s, double *fp_mul_per_s) {
+extern "C" int kzg_b200_measure_peaks(kzg_b200_ctx *ctx, double *imad_per_s, double *imad_wide_per_s,
+                                      double *fp_mul_per_s) {
     if (!ctx) return KZG_B200_BAD_ARGS;
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(cudaSetDevice(ctx->device));
@@ -452,6 +469,19 @@ extern "C" int kzg_b200_measure_peaks(kzg_b200_ctx *ctx, double *imad_per_s, dou
         cudaFree(d);
     }
     {
+        const int blocks = ctx->sms * 8, tpb = 256, iters = 4096;
+        uint64_t *d = nullptr;
+        CU(cudaMalloc(&d, (size_t)blocks * tpb * 8));
+        k_peak_imad_wide<<<blocks, tpb, 0, ctx->stream>>>(d, 64);
+        CU(cudaEventRecord(e0, ctx->stream));
+        k_peak_imad_wide<<<blocks, tpb, 0, ctx->stream>>>(d, iters);
+        CU(cudaEventRecord(e1, ctx->stream));
+        CU(cudaEventSynchronize(e1));
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (imad_wide_per_s) *imad_wide_per_s = (double)blocks * tpb * iters * 64.0 / (ms * 1e-3);
+        cudaFree(d);
+    }
+    {
         const int blocks = ctx->sms * KZG_ADD_MIN_BLOCKS, tpb = KZG_ADD_THREADS, iters = 2048;
         fp_t *d = nullptr;
         CU(cudaMalloc(&d, (size_t)blocks * tpb * sizeof(fp_t)));
@@ -464,9 +494,55 @@ extern "C" int kzg_b200_measure_peaks(kzg_b200_ctx *ctx, double *imad_per_s, dou
         if (fp_mul_per_s) *fp_mul_per_s = (double)blocks * tpb * iters * 2.0 / (ms * 1e-3);
         cudaFree(d);
     }
-    ctx->launches += 4;
+    ctx->launches += 6;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    return KZG_B200_OK;
+}
+
+// debugging aid (not declared in the public header): raw table entries, affine Montgomery limbs
+extern "C" int kzg_b200_debug_table(kzg_b200_ctx *ctx, uint64_t first, uint64_t count, void *out) {
+    if (!ctx) return KZG_B200_BAD_ARGS;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpy(out, ctx->d_table + first, count * sizeof(g1_affine_t), cudaMemcpyDeviceToHost));
+    return KZG_B200_OK;
+}
+
+// debugging / unit-test aid: device field operations on arrays (op 0: Fp mul, 1: Fp inverse (b ignored),
+// 2: Fr mul, 3: Fp add, 4: Fp sub).  Operands are raw limbs (12 or 8 words each).
+__global__ void k_debug_field_op(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, uint64_t count) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    if (op == 2) {
+        fr_t x, y, z;
+        for (int k = 0; k < 8; k++) { x.l[k] = a[8 * i + k]; y.l[k] = b[8 * i + k]; }
+        fe_mul(z, x, y);
+        for (int k = 0; k < 8; k++) out[8 * i + k] = z.l[k];
+        return;
+    }
+    fp_t x, y, z;
+    for (int k = 0; k < 12; k++) { x.l[k] = a[12 * i + k]; y.l[k] = b[12 * i + k]; }
+    if (op == 0) fe_mul(z, x, y);
+    else if (op == 1) fp_inv(z, x);
+    else if (op == 3) fe_add(z, x, y);
+    else fe_sub(z, x, y);
+    for (int k = 0; k < 12; k++) out[12 * i + k] = z.l[k];
+}
+extern "C" int kzg_b200_debug_field_op(kzg_b200_ctx *ctx, int op, const uint32_t *a, const uint32_t *b, uint32_t *out,
+                                       uint64_t count) {
+    if (!ctx) return KZG_B200_BAD_ARGS;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    size_t w = op == 2 ? 8 : 12;
+    uint32_t *d = nullptr;
+    CU(cudaMalloc(&d, 3 * count * w * 4));
+    CU(cudaMemcpy(d, a, count * w * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d + count * w, b, count * w * 4, cudaMemcpyHostToDevice));
+    k_debug_field_op<<<blocks_for(count, 128), 128, 0, ctx->stream>>>(op, d, d + count * w, d + 2 * count * w, count);
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(out, d + 2 * count * w, count * w * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d);
     return KZG_B200_OK;
 }
 

@@ -15,3 +15,11 @@ void shim_fr_sub(const uint32_t *a, const uint32_t *b, uint32_t *r) { fr_t x, y,
 void shim_fr_inv(const uint32_t *a, uint32_t *r) { fr_t x, z; memcpy(x.l, a, 32); fr_inv(z, x); memcpy(r, z.l, 32); }
 int shim_fr_canonical(const uint32_t *a) { fr_t x; memcpy(x.l, a, 32); return fr_is_canonical(x); }
 }
+extern "C" {
+void shim_fp_mul_many(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t count) {
+    for (size_t i = 0; i < count; i++) shim_fp_mul(a + 12 * i, b + 12 * i, r + 12 * i);
+}
+void shim_fr_mul_many(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t count) {
+    for (size_t i = 0; i < count; i++) shim_fr_mul(a + 8 * i, b + 8 * i, r + 8 * i);
+}
+}

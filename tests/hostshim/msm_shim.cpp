@@ -47,3 +47,20 @@ extern "C" int shim_commit(const uint8_t *g1_bytes, int n, int c, const uint8_t 
     for (int b = 0; b < B; b++) g1a_compress(out + 48 * b, in[b]);
     return 0;
 }
+
+// The precomputed table alone (same layout as the device table), for debugging / tests.
+extern "C" int shim_table(const uint8_t *g1_bytes, int n, int c, g1_affine_t *table, int T, int k) {
+    const int W = msm_num_windows(c);
+    const uint32_t D = 1u << (c - 1);
+    for (int i = 0; i < n; i++) {
+        g1_affine_t p;
+        if (g1_decode_thread(p, g1_bytes + 48 * bitrev(i, n), false)) return KZG_BADARGS;
+        table[(size_t)i * D] = p;
+    }
+    for (int i = 0; i < n; i++) window_base_thread(table, i, n, c, W, D);
+    for (int L = 0; L + 1 < c; L++) {
+        TableLevelPolicy pol{table, D, (uint32_t)L};
+        run_level(pol, (uint64_t)W * n << L, T, k);
+    }
+    return 0;
+}

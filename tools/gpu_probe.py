@@ -26,8 +26,8 @@ for c in cs:
     t0 = time.time()
     s = k.KzgSettings.load_trusted_setup(g.g1_bytes, g.g2_bytes, 0, c)
     t_create = time.time() - t0
-    imad, fpmul = ctypes.c_double(), ctypes.c_double()
-    L.kzg_b200_measure_peaks(s._h, ctypes.byref(imad), ctypes.byref(fpmul))
+    imad, imadw, fpmul = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    L.kzg_b200_measure_peaks(s._h, ctypes.byref(imad), ctypes.byref(imadw), ctypes.byref(fpmul))
     blobs = torch.from_numpy(synthetic_blobs(min(nblobs, 256), seed=3)).cuda()
     reps = (nblobs + blobs.shape[0] - 1) // blobs.shape[0]
     blobs = blobs.repeat(reps, 1)[:nblobs].contiguous()
@@ -41,7 +41,7 @@ for c in cs:
     rc = L.kzg_b200_blob_to_kzg_commitment_device(s._h, blobs.data_ptr(), nblobs, outb.data_ptr(), st.data_ptr())
     L.kzg_b200_synchronize(s._h)
     dt = time.time() - t0
-    rec = {"c": c, "create_s": t_create, "imad_per_s": imad.value, "fp_mul_per_s": fpmul.value,
+    rec = {"c": c, "create_s": t_create, "imad_per_s": imad.value, "imad_wide_per_s": imadw.value, "fp_mul_per_s": fpmul.value,
            "blobs": nblobs, "commit_s": dt, "blobs_per_s": nblobs / dt, "status_any": bool(st.any().item())}
     print(rec, flush=True)
     out["probe"].append(rec)
