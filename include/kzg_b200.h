@@ -140,6 +140,25 @@ int kzg_b200_blob_to_kzg_commitment_device(kzg_b200_ctx *ctx, const uint8_t *d_b
 int kzg_b200_compute_blob_kzg_proof_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments,
                                            size_t n, uint8_t *d_proofs_out, int32_t *d_status);
 int kzg_b200_synchronize(kzg_b200_ctx *ctx);
+/*
+ * Per-stage device timing of the calls on this context, measured with CUDA events on the
+ * context's stream (bench.py's roofline numbers come from here).  enable(1) resets the
+ * accumulators; read() waits for the stream and returns milliseconds / kernel launches per
+ * stage since then (arrays of KZG_B200_NUM_STAGES).
+ */
+enum {
+    KZG_B200_STAGE_DIGITS = 0,       /* blob bytes -> canonical check -> signed window digits */
+    KZG_B200_STAGE_MSM_GATHER = 1,   /* first level of the MSM: table gather + batched affine additions */
+    KZG_B200_STAGE_MSM_TREE = 2,     /* remaining levels of the addition tree */
+    KZG_B200_STAGE_COMPRESS = 3,     /* 48-byte compression */
+    KZG_B200_STAGE_CHALLENGE = 4,    /* per-blob SHA-256 Fiat-Shamir challenge */
+    KZG_B200_STAGE_EVAL = 5,         /* barycentric evaluation (+ quotient, digits) */
+    KZG_B200_STAGE_VALIDATE = 6,     /* G1 decompression + subgroup checks */
+    KZG_B200_STAGE_VERIFY_TERMS = 7, /* r-power scalar multiplications of batch verification */
+    KZG_B200_NUM_STAGES = 8
+};
+int kzg_b200_profile_enable(kzg_b200_ctx *ctx, int on);
+int kzg_b200_profile_read(kzg_b200_ctx *ctx, double *ms_out, uint64_t *launches_out);
 /* the CUDA stream (cudaStream_t) the context launches on, for event timing */
 void *kzg_b200_stream(kzg_b200_ctx *ctx);
 /* number of kernel launches issued by this context so far (bench.py reports the delta) */

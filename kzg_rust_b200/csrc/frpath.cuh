@@ -1,11 +1,19 @@
 // frpath.cuh -- scalar-field (Fr) side of the blob path: roots of unity, the Fiat-Shamir
-// challenge, barycentric evaluation and the quotient polynomial.
+// challenge, barycentric evaluation, the quotient polynomial and the r-power linear
+// combinations of batch verification.
+//
+//   k_challenge        reference compute_challenge              src/kzg.rs:298-339
+//   k_eval_quotient    evaluate_polynomial_in_evaluation_form   src/kzg.rs:346-389
+//                      + the quotient of compute_kzg_proof_impl src/kzg.rs:461-523
+//                      (both share one batch inversion: 1/(w_i - z) = -1/(z - w_i))
+//   k_load_scalars     bytes_to_bls_field                       src/utils.rs:262-275
 #pragma once
 #include <cuda_runtime.h>
 
 #include <vector>
 
 #include "blobpath.cuh"
+#include "sha256.cuh"
 
 namespace kzg {
 
@@ -34,5 +42,361 @@ inline int fr_setup_roots(int n, fr_t **d_roots, cudaStream_t stream) {
     if (cudaStreamSynchronize(stream) != cudaSuccess) return KZG_CUDA;
     return KZG_OK;
 }
+
+#if defined(__CUDACC__)
+
+KZG_D fr_t fr_inv_n_mont(int n) {
+    fr_t r;
+    constexpr uint32_t a[8] = {FR_INV_N_MONT_4096_LIMBS}, b[8] = {FR_INV_N_MONT_4_LIMBS};
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = n == 4096 ? a[i] : b[i];
+    return r;
+}
+KZG_D void ld_fr(fr_t &r, const fr_t *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = q[0], b = q[1];
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+}
+KZG_D void st_fr(fr_t *p, const fr_t &r) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(r.l[0], r.l[1], r.l[2], r.l[3]);
+    q[1] = make_uint4(r.l[4], r.l[5], r.l[6], r.l[7]);
+}
+// 32 bytes -> 8 big-endian message words
+KZG_D void ld_be_words8(uint32_t *w, const uint8_t *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = q[0], b = q[1];
+    w[0] = __byte_perm(a.x, 0, 0x0123); w[1] = __byte_perm(a.y, 0, 0x0123);
+    w[2] = __byte_perm(a.z, 0, 0x0123); w[3] = __byte_perm(a.w, 0, 0x0123);
+    w[4] = __byte_perm(b.x, 0, 0x0123); w[5] = __byte_perm(b.y, 0, 0x0123);
+    w[6] = __byte_perm(b.z, 0, 0x0123); w[7] = __byte_perm(b.w, 0, 0x0123);
+}
+KZG_D void st_scalar_be32(uint8_t *p, const fr_t &canon) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(__byte_perm(canon.l[7], 0, 0x0123), __byte_perm(canon.l[6], 0, 0x0123),
+                      __byte_perm(canon.l[5], 0, 0x0123), __byte_perm(canon.l[4], 0, 0x0123));
+    q[1] = make_uint4(__byte_perm(canon.l[3], 0, 0x0123), __byte_perm(canon.l[2], 0, 0x0123),
+                      __byte_perm(canon.l[1], 0, 0x0123), __byte_perm(canon.l[0], 0, 0x0123));
+}
+
+// ------------------------------------------------------------------ Fiat-Shamir challenge
+// One hash stream per blob: SHA-256("FSBLOBVERIFY_V1_" || u64be(0) || u64be(n) || blob ||
+// commitment) reduced mod r.  The message is 32 + 32 n + 48 bytes: block 0 carries the
+// 32-byte header and element 0, every further block two elements, the one after the last
+// element the first 32 commitment bytes, and the final block the last 16 commitment bytes
+// plus the padding.  The next block is loaded while the current one is compressed.
+// z_out: canonical little-endian limbs.
+__global__ void __launch_bounds__(64) k_challenge(const uint8_t *__restrict__ blobs, const uint8_t *__restrict__ commitments,
+                                                  uint32_t count, int n, fr_t *__restrict__ z_out) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= count) return;
+    const uint8_t *blob = blobs + (size_t)b * n * 32;
+    const uint8_t *cm = commitments + (size_t)b * 48;
+    uint32_t h[8], w[16], nx[16];
+    sha256_init(h);
+    w[0] = 0x4653424cu; w[1] = 0x4f425645u; w[2] = 0x52494659u; w[3] = 0x5f56315fu;  // "FSBLOBVERIFY_V1_"
+    w[4] = 0; w[5] = 0; w[6] = 0; w[7] = (uint32_t)n;
+    ld_be_words8(w + 8, blob);
+    const int pairs = n / 2;  // blocks 1 .. pairs-1 hold elements (2k-1, 2k)
+#pragma unroll 1
+    for (int k = 1; k < pairs; k++) {
+        ld_be_words8(nx, blob + 64 * (size_t)k - 32);
+        ld_be_words8(nx + 8, blob + 64 * (size_t)k);
+        sha256_compress(h, w);
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = nx[i];
+    }
+    ld_be_words8(nx, blob + 32 * (size_t)(n - 1));
+    ld_be_words8(nx + 8, cm);
+    sha256_compress(h, w);
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = nx[i];
+    sha256_compress(h, w);
+    {
+        const uint4 t = *reinterpret_cast<const uint4 *>(cm + 32);
+        w[0] = __byte_perm(t.x, 0, 0x0123); w[1] = __byte_perm(t.y, 0, 0x0123);
+        w[2] = __byte_perm(t.z, 0, 0x0123); w[3] = __byte_perm(t.w, 0, 0x0123);
+        w[4] = 0x80000000u;
+#pragma unroll
+        for (int i = 5; i < 14; i++) w[i] = 0;
+        uint64_t bits = (uint64_t)(32 + 32 * (uint64_t)n + 48) * 8;
+        w[14] = (uint32_t)(bits >> 32);
+        w[15] = (uint32_t)bits;
+    }
+    sha256_compress(h, w);
+    fr_t z;
+#pragma unroll
+    for (int i = 0; i < 8; i++) z.l[i] = h[7 - i];
+    scalar_reduce(z);
+    st_fr(z_out + b, z);
+}
+
+// caller-supplied evaluation points (compute_kzg_proof): 32 big-endian bytes each, must be
+// canonical (reference src/kzg.rs:452 -> bytes_to_bls_field)
+__global__ void k_load_scalars(const uint8_t *__restrict__ in, uint32_t count, fr_t *__restrict__ out, int32_t *status) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    fr_t s;
+    scalar_from_be32(s, in + 32ull * i);
+    if (!fr_is_canonical(s)) { atomicMax(status + i, (int)KZG_BADARGS); fe_set_zero(s); }
+    st_fr(out + i, s);
+}
+
+// ------------------------------------------------------------------ evaluation + quotient
+// One CTA per blob.  With d_i = z - w_i:
+//   y   = (z^n - 1)/n * sum_i p_i w_i / d_i                    (or p_m when z == w_m)
+//   q_i = (p_i - y)/(w_i - z) = (y - p_i)/d_i                  (i != m)
+//   q_m = 1/z * sum_{i != m} (p_i - y) w_i / d_i               (only when z == w_m)
+// The n inverses come from one Montgomery-trick inversion per CTA: thread-local prefix
+// products, a block-wide prefix and suffix scan of the per-thread totals, one field
+// inversion, and the unwinding.  inv[] (n per blob, global, L2-resident) holds the prefix
+// products and then the inverses.  QUOT = false stops after y (verification).
+// Outputs: zy_out (optional) = z || y as 32-byte big-endian records; digits (QUOT) = signed
+// window digits of the canonical q_i, ready for the MSM.
+#define KZG_EVAL_THREADS 256
+template <bool QUOT>
+__global__ void __launch_bounds__(KZG_EVAL_THREADS) k_eval_quotient(
+    const uint8_t *__restrict__ blobs, const fr_t *__restrict__ z_canon, const fr_t *__restrict__ roots, int n,
+    fr_t *__restrict__ inv, fr_t *__restrict__ poly, uint8_t *__restrict__ zy_out, int16_t *__restrict__ digits, int c,
+    int W, int32_t *status) {
+    constexpr int T = KZG_EVAL_THREADS;
+    __shared__ fr_t sh_pre[2][T];
+    __shared__ fr_t sh_suf[2][T];
+    __shared__ fr_t sh_val[2];
+    __shared__ int sh_m;
+    const int tid = threadIdx.x;
+    const uint32_t b = blockIdx.x;
+    const uint8_t *blob = blobs + (size_t)b * n * 32;
+    fr_t *binv = inv + (size_t)b * n, *bpoly = poly + (size_t)b * n;
+    const fr_t one = fe_one<FrParams>();
+    fr_t z;
+    ld_fr(z, z_canon + b);
+    if (zy_out && tid == 0) st_scalar_be32(zy_out + 64ull * b, z);
+    fe_to_mont(z, z);
+    if (tid == 0) sh_m = -1;
+    __syncthreads();
+    // pass 1: p_i, d_i, thread-local prefix products
+    fr_t run = one;
+#pragma unroll 1
+    for (int i = tid; i < n; i += T) {
+        fr_t s, p, d, w;
+        scalar_from_be32(s, blob + 32ull * i);
+        if (!fr_is_canonical(s)) { atomicMax(status + b, (int)KZG_BADARGS); fe_set_zero(s); }
+        fe_to_mont(p, s);
+        st_fr(bpoly + i, p);
+        ld_fr(w, roots + i);
+        fe_sub(d, z, w);
+        if (fe_is_zero(d)) { sh_m = i; d = one; }
+        st_fr(binv + i, run);
+        fe_mul(run, run, d);
+    }
+    sh_pre[0][tid] = run;
+    sh_suf[0][tid] = run;
+    __syncthreads();
+    // inclusive prefix and suffix products over the T per-thread totals
+    int cur = 0;
+#pragma unroll 1
+    for (int off = 1; off < T; off <<= 1) {
+        fr_t a = sh_pre[cur][tid], s = sh_suf[cur][tid];
+        if (tid >= off) fe_mul(a, sh_pre[cur][tid - off], a);
+        if (tid + off < T) fe_mul(s, s, sh_suf[cur][tid + off]);
+        sh_pre[cur ^ 1][tid] = a;
+        sh_suf[cur ^ 1][tid] = s;
+        cur ^= 1;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        fr_t t;
+        fr_inv(t, sh_pre[cur][T - 1]);
+        sh_val[0] = t;
+    }
+    __syncthreads();
+    const int m = sh_m;
+    fr_t inv_run = sh_val[0];
+    if (tid > 0) fe_mul(inv_run, inv_run, sh_pre[cur][tid - 1]);
+    if (tid + 1 < T) fe_mul(inv_run, inv_run, sh_suf[cur][tid + 1]);
+    // pass 2 (backwards): inverses and the barycentric sum
+    fr_t acc;
+    fe_set_zero(acc);
+    int last = tid + ((n - 1 - tid) / T) * T;  // largest i = tid (mod T) below n (negative range when tid >= n)
+#pragma unroll 1
+    for (int i = (tid < n ? last : -1); i >= 0; i -= T) {
+        fr_t w, d, pre, iv;
+        ld_fr(w, roots + i);
+        fe_sub(d, z, w);
+        if (i == m) d = one;
+        ld_fr(pre, binv + i);
+        fe_mul(iv, inv_run, pre);
+        fe_mul(inv_run, inv_run, d);
+        st_fr(binv + i, iv);
+        if (m < 0) {
+            fr_t p, t;
+            ld_fr(p, bpoly + i);
+            fe_mul(t, iv, w);
+            fe_mul(t, t, p);
+            fe_add(acc, acc, t);
+        }
+    }
+    __syncthreads();  // sh_pre is reused for the reduction
+    fr_t *red = sh_pre[0];
+    red[tid] = acc;
+    __syncthreads();
+#pragma unroll 1
+    for (int s = T / 2; s > 0; s >>= 1) {
+        if (tid < s) { fr_t t; fe_add(t, red[tid], red[tid + s]); red[tid] = t; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        fr_t y;
+        if (m >= 0) {
+            ld_fr(y, bpoly + m);
+        } else {
+            fr_t zn = z;
+            for (int k = 1; k < n; k <<= 1) fe_sqr(zn, zn);  // z^n, n a power of two
+            fe_sub(zn, zn, one);
+            fe_mul(y, red[0], zn);
+            fe_mul(y, y, fr_inv_n_mont(n));
+        }
+        sh_val[1] = y;
+        if (zy_out) {
+            fr_t yc;
+            fe_from_mont(yc, y);
+            st_scalar_be32(zy_out + 64ull * b + 32, yc);
+        }
+    }
+    __syncthreads();
+    if (!QUOT) return;
+    const fr_t y = sh_val[1];
+    int16_t *bdig = digits + (size_t)b * W * n;
+    fe_set_zero(acc);
+#pragma unroll 1
+    for (int i = tid; i < n; i += T) {
+        if (i == m) continue;
+        fr_t p, iv, q;
+        ld_fr(p, bpoly + i);
+        ld_fr(iv, binv + i);
+        fe_sub(q, y, p);
+        fe_mul(q, q, iv);
+        if (m >= 0) {
+            fr_t w, t;
+            ld_fr(w, roots + i);
+            fe_mul(t, q, w);      // = -(p_i - y) w_i / d_i
+            fe_sub(acc, acc, t);
+        }
+        fr_t qc;
+        fe_from_mont(qc, q);
+        recode_signed(qc, c, W, bdig + i, (uint64_t)n);
+    }
+    if (m >= 0) {  // uniform per CTA
+        __syncthreads();
+        red[tid] = acc;
+        __syncthreads();
+#pragma unroll 1
+        for (int s = T / 2; s > 0; s >>= 1) {
+            if (tid < s) { fr_t t; fe_add(t, red[tid], red[tid + s]); red[tid] = t; }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            fr_t zi, q, qc;
+            fr_inv(zi, z);  // z = w_m != 0
+            fe_mul(q, red[0], zi);
+            fe_from_mont(qc, q);
+            recode_signed(qc, c, W, bdig + m, (uint64_t)n);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ batch verification, phase B
+// Per blob i (global index first + i): r_i = r^(first+i) and the three products
+//   V_i = [r_i] proof_i,   U_i = [r_i] C_i + [r_i z_i] proof_i,   s_i = r_i y_i
+// (reference verify_kzg_proof_batch src/kzg.rs:579-627 and compute_r_powers
+// src/utils.rs:426-474; sum_i r_i [y_i]G is folded into one scalar).
+// Shamir's trick shares the doublings of the two multiplications that make up U_i.
+// out_pts[i] = V_i, out_pts[count + i] = U_i (affine), sy[i] = s_i (Montgomery).
+__global__ void __launch_bounds__(64) k_verify_terms(const g1_affine_t *__restrict__ cpts, const g1_affine_t *__restrict__ ppts,
+                                                     const uint8_t *__restrict__ zy, fr_t r_canon, uint64_t first,
+                                                     uint32_t count, g1_affine_t *__restrict__ out_pts, fr_t *__restrict__ sy) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    fr_t r, ri = fe_one<FrParams>();
+    fe_to_mont(r, r_canon);
+    {
+        uint64_t e = first + i;
+        fr_t base = r;
+#pragma unroll 1
+        while (e) {
+            if (e & 1) fe_mul(ri, ri, base);
+            fe_sqr(base, base);
+            e >>= 1;
+        }
+    }
+    fr_t z, y, t;
+    scalar_from_be32(z, zy + 64ull * i);
+    scalar_from_be32(y, zy + 64ull * i + 32);
+    fe_to_mont(z, z);
+    fe_to_mont(y, y);
+    fe_mul(t, ri, y);
+    st_fr(sy + i, t);
+    fr_t ka, kb;
+    fe_mul(kb, ri, z);
+    fe_from_mont(ka, ri);
+    fe_from_mont(kb, kb);
+    g1_affine_t C = cpts[i], P = ppts[i];
+    const bool c_inf = g1a_is_inf(C), p_inf = g1a_is_inf(P);
+    g1_jac_t V, U;
+    g1j_set_inf(V);
+    g1j_set_inf(U);
+#pragma unroll 1
+    for (int bit = 254; bit >= 0; bit--) {
+        g1j_dbl(V, V);
+        g1j_dbl(U, U);
+        const bool ba = (ka.l[bit >> 5] >> (bit & 31)) & 1, bb = (kb.l[bit >> 5] >> (bit & 31)) & 1;
+        if (ba && !p_inf) g1j_add_affine(V, V, P.x, P.y);
+        if (ba && !c_inf) g1j_add_affine(U, U, C.x, C.y);
+        if (bb && !p_inf) g1j_add_affine(U, U, P.x, P.y);
+    }
+    g1_affine_t a;
+    g1j_to_affine(a, V);
+    out_pts[i] = a;
+    g1j_to_affine(a, U);
+    out_pts[count + i] = a;
+}
+// sum of `count` Montgomery scalars -> out[0] (one CTA)
+__global__ void __launch_bounds__(256) k_fr_sum(const fr_t *__restrict__ in, uint32_t count, fr_t *__restrict__ out) {
+    __shared__ fr_t red[256];
+    fr_t acc;
+    fe_set_zero(acc);
+    for (uint32_t i = threadIdx.x; i < count; i += 256) { fr_t t; ld_fr(t, in + i); fe_add(acc, acc, t); }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) { fr_t t; fe_add(t, red[threadIdx.x], red[threadIdx.x + s]); red[threadIdx.x] = t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
+}
+// partial record of one shard: A (96 B) || B (96 B) || s (32 B); points as uncompressed
+// big-endian affine coordinates, bit 6 of byte 0 set for infinity
+__global__ void k_write_partial(const g1_affine_t *__restrict__ ab, const fr_t *__restrict__ s, uint8_t *__restrict__ out) {
+    if (threadIdx.x < 2) {
+        g1_affine_t p = ab[threadIdx.x];
+        uint8_t *o = out + 96 * threadIdx.x;
+        if (g1a_is_inf(p)) {
+            for (int i = 0; i < 96; i++) o[i] = 0;
+            o[0] = 0x40;
+        } else {
+            fp_t c;
+            fe_from_mont(c, p.x); fp_to_be48(o, c);
+            fe_from_mont(c, p.y); fp_to_be48(o + 48, c);
+        }
+    } else if (threadIdx.x == 2) {
+        fr_t c;
+        fe_from_mont(c, s[0]);
+        scalar_to_be32(out + 192, c);
+    }
+}
+
+#endif  // __CUDACC__
 
 }  // namespace kzg

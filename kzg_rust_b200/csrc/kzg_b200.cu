@@ -58,23 +58,59 @@ struct kzg_b200_ctx {
     uint8_t *d_stage_aux = nullptr;   // chunk x 96 B (commitments / proofs / z)
     uint8_t *d_stage_out = nullptr;   // chunk x 96 B
     int32_t *d_status = nullptr;
-    fr_t *d_poly = nullptr;           // chunk x n (proof / verify paths)
-    fr_t *d_zy = nullptr;             // chunk x 2
+    fr_t *d_poly = nullptr;           // chunk x n Montgomery evaluations (proof / verify paths)
+    fr_t *d_inv = nullptr;            // chunk x n prefix products, then 1/(z - w_i)
+    fr_t *d_z = nullptr;              // chunk challenges / evaluation points (canonical)
+    uint8_t *d_zy = nullptr;          // chunk x 64 B: z || y big-endian
     g1_affine_t *d_pts = nullptr;     // chunk x 2 decoded commitments / proofs
+    host_g2_prepared *tau_prepared = nullptr;  // Miller-loop lines of [tau]G2
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
+    // optional per-stage device timing (CUDA events on `stream`), see kzg_b200_profile_*
+    bool profile = false;
+    struct StageRec { int stage; cudaEvent_t a, b; };
+    std::vector<StageRec> pending;
+    double stage_ms[KZG_B200_NUM_STAGES] = {0};
+    uint64_t stage_launches[KZG_B200_NUM_STAGES] = {0};
     std::mutex mu;
 };
 
+// ------------------------------------------------------------------ stage timing
+static void stage_begin(kzg_b200_ctx *ctx, int stage) {
+    if (!ctx->profile) return;
+    kzg_b200_ctx::StageRec r;
+    r.stage = stage;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, ctx->stream);
+    ctx->pending.push_back(r);
+}
+static void stage_end(kzg_b200_ctx *ctx, uint64_t launches) {
+    if (!ctx->profile || ctx->pending.empty()) return;
+    cudaEventRecord(ctx->pending.back().b, ctx->stream);
+    ctx->stage_launches[ctx->pending.back().stage] += launches;
+}
+static void stage_collect(kzg_b200_ctx *ctx) {  // stream must be idle
+    for (auto &r : ctx->pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) ctx->stage_ms[r.stage] += ms;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    ctx->pending.clear();
+}
+
 // ------------------------------------------------------------------ kernels
+// status slot of point i is i % status_mod (commitments and proofs of one chunk are decoded by one
+// launch and share the per-blob status)
 __global__ void k_decode_g1(const uint8_t *in, g1_affine_t *out, int32_t *status, uint32_t count, int check_subgroup,
-                            int status_stride) {
+                            uint32_t status_mod) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     g1_affine_t p;
     int rc = g1_decode_thread(p, in + 48ull * i, check_subgroup != 0);
     out[i] = p;
-    if (rc != KZG_OK && status) atomicMax(status + (size_t)i * status_stride, rc);
+    if (rc != KZG_OK && status) atomicMax(status + (i % status_mod), rc);
 }
 // table[i*D] = decoded[bitrev(i)]   (reference bit_reversal_permutation, src/kzg.rs:717-731)
 __global__ void k_place_bases(const g1_affine_t *decoded, g1_affine_t *table, uint32_t n, uint32_t D) {
@@ -136,23 +172,38 @@ __global__ void k_peak_imad(uint32_t *out, int iters) {
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
 }
+// 32x32+64 multiply-adds in carry chains (mad.lo.cc / madc.hi.cc pairs -> IMAD.WIDE.U32.X), the
+// form the field multiplication uses; the multiplier depends on the running value so ptxas
+// cannot strength-reduce it.  32 wide MACs per inner step.
 __global__ void k_peak_imad_wide(uint64_t *out, int iters) {
-    uint32_t a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 3;
-    uint64_t x0 = a, x1 = a + 1, x2 = a + 2, x3 = a + 3, x4 = a + 4, x5 = a + 5, x6 = a + 6, x7 = a + 7;
+    uint32_t a[8], c[16];
+    for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 2654435761u + i;
+    for (int i = 0; i < 16; i++) c[i] = i;
+    uint32_t b = blockIdx.x * 40503u + 3;
 #pragma unroll 1
-    for (int i = 0; i < iters; i++) {
+    for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\tmad.wide.u32 %2, %8, %9, %2;\n\t"
-                         "mad.wide.u32 %3, %8, %9, %3;\n\tmad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\t"
-                         "mad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
-                         : "+l"(x0), "+l"(x1), "+l"(x2), "+l"(x3), "+l"(x4), "+l"(x5), "+l"(x6), "+l"(x7)
-                         : "r"(b), "r"(a));
+        for (int u = 0; u < 4; u++) {
+            uint32_t m = c[0] ^ b;
+            asm volatile(
+                "mad.lo.cc.u32 %0, %16, %24, %0;\n\tmadc.hi.cc.u32 %1, %16, %24, %1;\n\t"
+                "madc.lo.cc.u32 %2, %17, %24, %2;\n\tmadc.hi.cc.u32 %3, %17, %24, %3;\n\t"
+                "madc.lo.cc.u32 %4, %18, %24, %4;\n\tmadc.hi.cc.u32 %5, %18, %24, %5;\n\t"
+                "madc.lo.cc.u32 %6, %19, %24, %6;\n\tmadc.hi.u32 %7, %19, %24, %7;\n\t"
+                "mad.lo.cc.u32 %8, %20, %24, %8;\n\tmadc.hi.cc.u32 %9, %20, %24, %9;\n\t"
+                "madc.lo.cc.u32 %10, %21, %24, %10;\n\tmadc.hi.cc.u32 %11, %21, %24, %11;\n\t"
+                "madc.lo.cc.u32 %12, %22, %24, %12;\n\tmadc.hi.cc.u32 %13, %22, %24, %13;\n\t"
+                "madc.lo.cc.u32 %14, %23, %24, %14;\n\tmadc.hi.u32 %15, %23, %24, %15;"
+                : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7]),
+                  "+r"(c[8]), "+r"(c[9]), "+r"(c[10]), "+r"(c[11]), "+r"(c[12]), "+r"(c[13]), "+r"(c[14]), "+r"(c[15])
+                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(m));
         }
     }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+    uint32_t x = 0;
+    for (int i = 0; i < 16; i++) x ^= c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
 }
-__global__ void __launch_bounds__(KZG_ADD_THREADS, KZG_ADD_MIN_BLOCKS) k_peak_fpmul(fp_t *out, int iters) {
+__global__ void __launch_bounds__(128, 4) k_peak_fpmul(fp_t *out, int iters) {
     fp_t x = fe_one<FpParams>(), y = fp_const_b();
     x.l[0] += threadIdx.x;
     y.l[1] ^= blockIdx.x;
@@ -204,15 +255,21 @@ static int launch_batch_add(kzg_b200_ctx *ctx, const Policy &pol, uint64_t total
 static int run_msm(kzg_b200_ctx *ctx, size_t count, const g1_affine_t **out) {
     uint32_t per_blob = (uint32_t)ctx->W * ctx->n, cnt = per_blob / 2;
     GatherPolicy gp{ctx->d_table, ctx->d_digits, ctx->d_buf_a, per_blob, ctx->D};
+    stage_begin(ctx, KZG_B200_STAGE_MSM_GATHER);
     RC(launch_batch_add(ctx, gp, (uint64_t)count * cnt));
+    stage_end(ctx, 1);
     g1_affine_t *in = ctx->d_buf_a, *o = ctx->d_buf_b;
+    stage_begin(ctx, KZG_B200_STAGE_MSM_TREE);
+    uint64_t levels = 0;
     while (cnt > 1) {
         uint32_t nxt = (cnt + 1) / 2;
         TreePolicy tp{in, o, cnt, nxt};
         RC(launch_batch_add(ctx, tp, (uint64_t)count * nxt));
         std::swap(in, o);
         cnt = nxt;
+        levels++;
     }
+    stage_end(ctx, levels);
     *out = in;
     return KZG_B200_OK;
 }
@@ -221,15 +278,15 @@ static int run_msm(kzg_b200_ctx *ctx, size_t count, const g1_affine_t **out) {
 static size_t per_blob_workspace(const kzg_b200_ctx *ctx) {
     size_t wn = (size_t)ctx->W * ctx->n;
     return wn * 2 /*digits*/ + wn / 2 * sizeof(g1_affine_t) + (wn / 4 + 1) * sizeof(g1_affine_t) +
-           (size_t)ctx->n * 32 /*stage in*/ + (size_t)ctx->n * sizeof(fr_t) /*poly*/ + 96 * 2 + 2 * sizeof(fr_t) +
+           (size_t)ctx->n * 32 /*stage in*/ + 2 * (size_t)ctx->n * sizeof(fr_t) /*poly, inv*/ + 96 * 2 + 64 + sizeof(fr_t) +
            2 * sizeof(g1_affine_t) + 4;
 }
 static void free_workspace(kzg_b200_ctx *ctx) {
     cudaFree(ctx->d_digits); cudaFree(ctx->d_buf_a); cudaFree(ctx->d_buf_b); cudaFree(ctx->d_stage_in);
     cudaFree(ctx->d_stage_aux); cudaFree(ctx->d_stage_out); cudaFree(ctx->d_status); cudaFree(ctx->d_poly);
-    cudaFree(ctx->d_zy); cudaFree(ctx->d_pts);
+    cudaFree(ctx->d_inv); cudaFree(ctx->d_z); cudaFree(ctx->d_zy); cudaFree(ctx->d_pts);
     ctx->d_digits = nullptr; ctx->d_buf_a = ctx->d_buf_b = nullptr; ctx->d_stage_in = ctx->d_stage_aux = ctx->d_stage_out = nullptr;
-    ctx->d_status = nullptr; ctx->d_poly = nullptr; ctx->d_zy = nullptr; ctx->d_pts = nullptr;
+    ctx->d_status = nullptr; ctx->d_poly = nullptr; ctx->d_inv = nullptr; ctx->d_z = nullptr; ctx->d_zy = nullptr; ctx->d_pts = nullptr;
     ctx->chunk = 0;
 }
 static int alloc_workspace(kzg_b200_ctx *ctx, size_t chunk) {
@@ -243,7 +300,9 @@ static int alloc_workspace(kzg_b200_ctx *ctx, size_t chunk) {
     CU(cudaMalloc(&ctx->d_stage_out, chunk * 96));
     CU(cudaMalloc(&ctx->d_status, chunk * sizeof(int32_t)));
     CU(cudaMalloc(&ctx->d_poly, chunk * (size_t)ctx->n * sizeof(fr_t)));
-    CU(cudaMalloc(&ctx->d_zy, chunk * 2 * sizeof(fr_t)));
+    CU(cudaMalloc(&ctx->d_inv, chunk * (size_t)ctx->n * sizeof(fr_t)));
+    CU(cudaMalloc(&ctx->d_z, chunk * sizeof(fr_t)));
+    CU(cudaMalloc(&ctx->d_zy, chunk * 64));
     CU(cudaMalloc(&ctx->d_pts, chunk * 2 * sizeof(g1_affine_t)));
     ctx->chunk = chunk;
     return KZG_B200_OK;
@@ -266,7 +325,7 @@ static int build_table(kzg_b200_ctx *ctx, const uint8_t *g1_bytes) {
     CU(cudaMemcpyAsync(d_bytes, g1_bytes, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(d_st, 0, (size_t)n * sizeof(int32_t), ctx->stream));
     // reference load_trusted_setup does not subgroup-check the G1 points (src/kzg.rs:859-872)
-    k_decode_g1<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(d_bytes, d_dec, d_st, n, 0, 1);
+    k_decode_g1<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(d_bytes, d_dec, d_st, n, 0, (uint32_t)n);
     ctx->launches++;
     std::vector<int32_t> st(n);
     CU(cudaMemcpyAsync(st.data(), d_st, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -305,6 +364,8 @@ extern "C" int kzg_b200_ctx_create(const uint8_t *g1_lagrange, size_t n1, const 
     ctx->device = device;
     ctx->n = (int)n1;
     memcpy(ctx->g2_tau, g2_monomial + 96, 96);
+    ctx->tau_prepared = host_g2_prepare(ctx->g2_tau);
+    if (!ctx->tau_prepared) { delete ctx; return KZG_B200_BAD_ARGS; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return KZG_B200_CUDA_ERROR; }
     ctx->sms = prop.multiProcessorCount;
@@ -387,6 +448,8 @@ extern "C" void kzg_b200_ctx_destroy(kzg_b200_ctx *ctx) {
     cudaFree(ctx->d_table);
     cudaFree(ctx->d_roots);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    stage_collect(ctx);
+    host_g2_prepared_free(ctx->tau_prepared);
     delete ctx;
 }
 extern "C" size_t kzg_b200_field_elements_per_blob(const kzg_b200_ctx *ctx) { return ctx ? (size_t)ctx->n : 0; }
@@ -397,6 +460,30 @@ extern "C" int kzg_b200_synchronize(kzg_b200_ctx *ctx) {
     if (!ctx) return KZG_B200_BAD_ARGS;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    stage_collect(ctx);
+    return KZG_B200_OK;
+}
+extern "C" int kzg_b200_profile_enable(kzg_b200_ctx *ctx, int on) {
+    if (!ctx) return KZG_B200_BAD_ARGS;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    stage_collect(ctx);
+    ctx->profile = on != 0;
+    for (int i = 0; i < KZG_B200_NUM_STAGES; i++) { ctx->stage_ms[i] = 0; ctx->stage_launches[i] = 0; }
+    return KZG_B200_OK;
+}
+extern "C" int kzg_b200_profile_read(kzg_b200_ctx *ctx, double *ms_out, uint64_t *launches_out) {
+    if (!ctx) return KZG_B200_BAD_ARGS;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    stage_collect(ctx);
+    for (int i = 0; i < KZG_B200_NUM_STAGES; i++) {
+        if (ms_out) ms_out[i] = ctx->stage_ms[i];
+        if (launches_out) launches_out[i] = ctx->stage_launches[i];
+    }
     return KZG_B200_OK;
 }
 
@@ -405,11 +492,15 @@ extern "C" int kzg_b200_synchronize(kzg_b200_ctx *ctx) {
 static int commit_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, size_t count, uint8_t *d_out, int32_t *d_status) {
     const uint64_t elems = (uint64_t)count * ctx->n;
     CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), ctx->stream));
+    stage_begin(ctx, KZG_B200_STAGE_DIGITS);
     k_blob_digits<<<blocks_for(elems, 256), 256, 0, ctx->stream>>>(d_blobs, elems, ctx->n, ctx->c, ctx->W, ctx->d_digits, d_status);
+    stage_end(ctx, 1);
     ctx->launches++;
     const g1_affine_t *res = nullptr;
     RC(run_msm(ctx, count, &res));
+    stage_begin(ctx, KZG_B200_STAGE_COMPRESS);
     k_compress<<<blocks_for(count, 64), 64, 0, ctx->stream>>>(res, d_status, d_out, (uint32_t)count);
+    stage_end(ctx, 1);
     ctx->launches++;
     CU(cudaGetLastError());
     return KZG_B200_OK;
@@ -478,11 +569,11 @@ extern "C" int kzg_b200_measure_peaks(kzg_b200_ctx *ctx, double *imad_per_s, dou
         CU(cudaEventRecord(e1, ctx->stream));
         CU(cudaEventSynchronize(e1));
         CU(cudaEventElapsedTime(&ms, e0, e1));
-        if (imad_wide_per_s) *imad_wide_per_s = (double)blocks * tpb * iters * 64.0 / (ms * 1e-3);
+        if (imad_wide_per_s) *imad_wide_per_s = (double)blocks * tpb * iters * 32.0 / (ms * 1e-3);
         cudaFree(d);
     }
     {
-        const int blocks = ctx->sms * KZG_ADD_MIN_BLOCKS, tpb = KZG_ADD_THREADS, iters = 2048;
+        const int blocks = ctx->sms * 4, tpb = 128, iters = 2048;
         fp_t *d = nullptr;
         CU(cudaMalloc(&d, (size_t)blocks * tpb * sizeof(fp_t)));
         k_peak_fpmul<<<blocks, tpb, 0, ctx->stream>>>(d, 16);

@@ -1,10 +1,278 @@
-// proof / verify entry points (first slice: not yet wired)
-extern "C" int kzg_b200_compute_blob_kzg_proof_batch(kzg_b200_ctx *, const uint8_t *, const uint8_t *, size_t, uint8_t *, int32_t *) { return KZG_B200_INTERNAL_ERROR; }
-extern "C" int kzg_b200_compute_kzg_proof_batch(kzg_b200_ctx *, const uint8_t *, const uint8_t *, size_t, uint8_t *, uint8_t *, int32_t *) { return KZG_B200_INTERNAL_ERROR; }
-extern "C" int kzg_b200_verify_blob_kzg_proof_batch(kzg_b200_ctx *, const uint8_t *, const uint8_t *, const uint8_t *, size_t, int *) { return KZG_B200_INTERNAL_ERROR; }
-extern "C" int kzg_b200_verify_phase_a(kzg_b200_ctx *, const uint8_t *, const uint8_t *, const uint8_t *, size_t, uint8_t *) { return KZG_B200_INTERNAL_ERROR; }
-extern "C" int kzg_b200_compute_r(const kzg_b200_ctx *, const uint8_t *, const uint8_t *, const uint8_t *, size_t, uint8_t *) { return KZG_B200_INTERNAL_ERROR; }
-extern "C" int kzg_b200_verify_phase_b(kzg_b200_ctx *, const uint8_t *, const uint8_t *, const uint8_t *, size_t, const uint8_t *, uint64_t, uint8_t *) { return KZG_B200_INTERNAL_ERROR; }
-extern "C" int kzg_b200_verify_finish(const kzg_b200_ctx *, const uint8_t *, size_t, int *) { return KZG_B200_INTERNAL_ERROR; }
-extern "C" int kzg_b200_compute_blob_kzg_proof_device(kzg_b200_ctx *, const uint8_t *, const uint8_t *, size_t, uint8_t *, int32_t *) { return KZG_B200_INTERNAL_ERROR; }
-extern "C" int kzg_b200_pairings_verify(const uint8_t a1[48], const uint8_t a2[96], const uint8_t b1[48], const uint8_t b2[96], int *ok) { return host_pairings_verify(a1, a2, b1, b2, ok); }
+// proof_verify.inl -- host sequencing of the proof and verification paths (included by
+// kzg_b200.cu).  Kernels live in frpath.cuh / msm.cuh; the only host arithmetic is the
+// SHA-256 of compute_r and the final pairing check (host_pairing.cpp).
+
+static int decode_points(kzg_b200_ctx *ctx, const uint8_t *d_bytes, g1_affine_t *d_out, int32_t *d_status, size_t count,
+                         int check_subgroup, size_t status_mod) {
+    stage_begin(ctx, KZG_B200_STAGE_VALIDATE);
+    k_decode_g1<<<blocks_for(count, 64), 64, 0, ctx->stream>>>(d_bytes, d_out, d_status, (uint32_t)count, check_subgroup,
+                                                               (uint32_t)status_mod);
+    stage_end(ctx, 1);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return KZG_B200_OK;
+}
+
+// ------------------------------------------------------------------ compute_blob_kzg_proof / compute_kzg_proof
+// One chunk on the device.  Exactly one of d_commitments (blob proof: z from the Fiat-Shamir
+// hash, reference src/kzg.rs:533-544) and d_zbytes (proof at a caller-supplied point,
+// src/kzg.rs:446-457) is non-null.  d_zy (optional) receives z || y.
+static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments, const uint8_t *d_zbytes,
+                       size_t count, uint8_t *d_proofs, uint8_t *d_zy, int32_t *d_status) {
+    CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), ctx->stream));
+    if (d_commitments) {
+        RC(decode_points(ctx, d_commitments, ctx->d_pts, d_status, count, 1, count));
+        stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
+        k_challenge<<<blocks_for(count, 64), 64, 0, ctx->stream>>>(d_blobs, d_commitments, (uint32_t)count, ctx->n, ctx->d_z);
+        stage_end(ctx, 1);
+    } else {
+        k_load_scalars<<<blocks_for(count, 128), 128, 0, ctx->stream>>>(d_zbytes, (uint32_t)count, ctx->d_z, d_status);
+    }
+    ctx->launches++;
+    stage_begin(ctx, KZG_B200_STAGE_EVAL);
+    k_eval_quotient<true><<<(unsigned)count, KZG_EVAL_THREADS, 0, ctx->stream>>>(
+        d_blobs, ctx->d_z, ctx->d_roots, ctx->n, ctx->d_inv, ctx->d_poly, d_zy, ctx->d_digits, ctx->c, ctx->W, d_status);
+    stage_end(ctx, 1);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    const g1_affine_t *res = nullptr;
+    RC(run_msm(ctx, count, &res));
+    stage_begin(ctx, KZG_B200_STAGE_COMPRESS);
+    k_compress<<<blocks_for(count, 64), 64, 0, ctx->stream>>>(res, d_status, d_proofs, (uint32_t)count);
+    stage_end(ctx, 1);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return KZG_B200_OK;
+}
+
+extern "C" int kzg_b200_compute_blob_kzg_proof_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments,
+                                                      size_t n, uint8_t *d_proofs_out, int32_t *d_status) {
+    if (!ctx || (n && (!d_blobs || !d_commitments || !d_proofs_out || !d_status))) return KZG_B200_BAD_ARGS;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const size_t bpb = (size_t)ctx->n * 32;
+    for (size_t off = 0; off < n; off += ctx->chunk) {
+        size_t cnt = std::min(ctx->chunk, n - off);
+        RC(proof_chunk(ctx, d_blobs + off * bpb, d_commitments + off * 48, nullptr, cnt, d_proofs_out + off * 48, nullptr,
+                       d_status + off));
+    }
+    return KZG_B200_OK;
+}
+
+extern "C" int kzg_b200_compute_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments,
+                                                     size_t n, uint8_t *proofs_out, int32_t *status) {
+    if (!ctx || (n && (!blobs || !commitments || !proofs_out || !status))) return KZG_B200_BAD_ARGS;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const size_t bpb = (size_t)ctx->n * 32;
+    for (size_t off = 0; off < n; off += ctx->chunk) {
+        size_t cnt = std::min(ctx->chunk, n - off);
+        CU(cudaMemcpyAsync(ctx->d_stage_in, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_stage_aux, commitments + off * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->stream));
+        RC(proof_chunk(ctx, ctx->d_stage_in, ctx->d_stage_aux, nullptr, cnt, ctx->d_stage_out, nullptr, ctx->d_status));
+        CU(cudaMemcpyAsync(proofs_out + off * 48, ctx->d_stage_out, cnt * 48, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(status + off, ctx->d_status, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    stage_collect(ctx);
+    return KZG_B200_OK;
+}
+
+extern "C" int kzg_b200_compute_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *z, size_t n,
+                                                uint8_t *proofs_out, uint8_t *y_out, int32_t *status) {
+    if (!ctx || (n && (!blobs || !z || !proofs_out || !y_out || !status))) return KZG_B200_BAD_ARGS;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const size_t bpb = (size_t)ctx->n * 32;
+    std::vector<uint8_t> zy;
+    for (size_t off = 0; off < n; off += ctx->chunk) {
+        size_t cnt = std::min(ctx->chunk, n - off);
+        zy.resize(cnt * 64);
+        CU(cudaMemcpyAsync(ctx->d_stage_in, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_stage_aux, z + off * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->stream));
+        RC(proof_chunk(ctx, ctx->d_stage_in, nullptr, ctx->d_stage_aux, cnt, ctx->d_stage_out, ctx->d_zy, ctx->d_status));
+        CU(cudaMemcpyAsync(proofs_out + off * 48, ctx->d_stage_out, cnt * 48, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(zy.data(), ctx->d_zy, cnt * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(status + off, ctx->d_status, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < cnt; i++) {
+            if (status[off + i] == KZG_B200_OK) memcpy(y_out + (off + i) * 32, zy.data() + 64 * i + 32, 32);
+            else memset(y_out + (off + i) * 32, 0, 32);
+        }
+    }
+    stage_collect(ctx);
+    return KZG_B200_OK;
+}
+
+// ------------------------------------------------------------------ verify_blob_kzg_proof_batch
+// Phase A (reference src/kzg.rs:671-683, per blob): validate C_i and proof_i, z_i, y_i.
+static int verify_phase_a_locked(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments, const uint8_t *proofs,
+                                 size_t n, uint8_t *zy_out) {
+    const size_t bpb = (size_t)ctx->n * 32;
+    std::vector<int32_t> st;
+    int rc = KZG_B200_OK;
+    for (size_t off = 0; off < n; off += ctx->chunk) {
+        size_t cnt = std::min(ctx->chunk, n - off);
+        st.resize(cnt);
+        CU(cudaMemcpyAsync(ctx->d_stage_in, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_stage_aux, commitments + off * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_stage_aux + cnt * 48, proofs + off * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_status, 0, cnt * sizeof(int32_t), ctx->stream));
+        RC(decode_points(ctx, ctx->d_stage_aux, ctx->d_pts, ctx->d_status, 2 * cnt, 1, cnt));
+        stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
+        k_challenge<<<blocks_for(cnt, 64), 64, 0, ctx->stream>>>(ctx->d_stage_in, ctx->d_stage_aux, (uint32_t)cnt, ctx->n, ctx->d_z);
+        stage_end(ctx, 1);
+        stage_begin(ctx, KZG_B200_STAGE_EVAL);
+        k_eval_quotient<false><<<(unsigned)cnt, KZG_EVAL_THREADS, 0, ctx->stream>>>(
+            ctx->d_stage_in, ctx->d_z, ctx->d_roots, ctx->n, ctx->d_inv, ctx->d_poly, ctx->d_zy, nullptr, ctx->c, ctx->W,
+            ctx->d_status);
+        stage_end(ctx, 1);
+        ctx->launches += 2;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(zy_out + off * 64, ctx->d_zy, cnt * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(st.data(), ctx->d_status, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < cnt; i++)
+            if (st[i] != KZG_B200_OK) rc = KZG_B200_BAD_ARGS;
+    }
+    stage_collect(ctx);
+    return rc;
+}
+extern "C" int kzg_b200_verify_phase_a(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments,
+                                       const uint8_t *proofs, size_t n, uint8_t *zy_out) {
+    if (!ctx || (n && (!blobs || !commitments || !proofs || !zy_out))) return KZG_B200_BAD_ARGS;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    return verify_phase_a_locked(ctx, blobs, commitments, proofs, n, zy_out);
+}
+
+// reference compute_r_powers (src/utils.rs:426-474), the hash only: the points are hashed in
+// their compressed form, which for a validated point is the caller's own 48 bytes.
+extern "C" int kzg_b200_compute_r(const kzg_b200_ctx *ctx, const uint8_t *commitments, const uint8_t *zy,
+                                  const uint8_t *proofs, size_t n_total, uint8_t r_out[32]) {
+    if (!ctx || !r_out || (n_total && (!commitments || !zy || !proofs))) return KZG_B200_BAD_ARGS;
+    Sha256 h;
+    h.init();
+    h.update((const uint8_t *)"RCKZGBATCH___V1_", 16);
+    uint8_t u[8];
+    for (int i = 0; i < 8; i++) u[i] = (uint8_t)((uint64_t)ctx->n >> (56 - 8 * i));
+    h.update(u, 8);
+    for (int i = 0; i < 8; i++) u[i] = (uint8_t)((uint64_t)n_total >> (56 - 8 * i));
+    h.update(u, 8);
+    for (size_t i = 0; i < n_total; i++) {
+        h.update(commitments + 48 * i, 48);
+        h.update(zy + 64 * i, 64);
+        h.update(proofs + 48 * i, 48);
+    }
+    uint8_t d[32];
+    h.finish(d);
+    fr_t r;
+    scalar_from_be32(r, d);
+    scalar_reduce(r);
+    scalar_to_be32(r_out, r);
+    return KZG_B200_OK;
+}
+
+// Phase B: the r-power linear combinations of one shard (reference src/kzg.rs:601-622).
+static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, const uint8_t *zy, const uint8_t *proofs,
+                                 size_t n, const uint8_t r[32], uint64_t first_index, uint8_t partial_out[224]) {
+    if (n == 0) {
+        memset(partial_out, 0, 224);
+        partial_out[0] = 0x40;
+        partial_out[96] = 0x40;
+        return KZG_B200_OK;
+    }
+    fr_t rc;
+    scalar_from_be32(rc, r);
+    if (!fr_is_canonical(rc)) return KZG_B200_BAD_ARGS;
+    // one allocation: bytes (48 + 48 + 64) n | status 2n | points 2n | terms 2n | tree n + 2 | sy n + 1 | partial
+    const size_t o_c = 0, o_p = o_c + 48 * n, o_zy = o_p + 48 * n;
+    size_t o_st = (o_zy + 64 * n + 15) / 16 * 16;
+    size_t o_pts = (o_st + 2 * n * sizeof(int32_t) + 15) / 16 * 16;
+    size_t o_terms = o_pts + 2 * n * sizeof(g1_affine_t);
+    size_t o_tree = o_terms + 2 * n * sizeof(g1_affine_t);
+    size_t o_sy = o_tree + (n + 2) * sizeof(g1_affine_t);
+    size_t o_part = o_sy + (n + 1) * sizeof(fr_t);
+    size_t total = o_part + 256;
+    uint8_t *d = nullptr;
+    CU(cudaMalloc(&d, total));
+    struct Free { uint8_t *p; ~Free() { cudaFree(p); } } guard{d};
+    CU(cudaMemcpyAsync(d + o_c, commitments, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d + o_p, proofs, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d + o_zy, zy, 64 * n, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t *d_st = (int32_t *)(d + o_st);
+    g1_affine_t *pts = (g1_affine_t *)(d + o_pts), *terms = (g1_affine_t *)(d + o_terms), *tree = (g1_affine_t *)(d + o_tree);
+    fr_t *sy = (fr_t *)(d + o_sy);
+    CU(cudaMemsetAsync(d_st, 0, 2 * n * sizeof(int32_t), ctx->stream));
+    // c and p byte arrays are contiguous: decode both with one launch (phase A did the subgroup checks)
+    RC(decode_points(ctx, d + o_c, pts, d_st, 2 * n, 0, 2 * n));
+    stage_begin(ctx, KZG_B200_STAGE_VERIFY_TERMS);
+    k_verify_terms<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(pts, pts + n, d + o_zy, rc, first_index, (uint32_t)n, terms, sy);
+    stage_end(ctx, 1);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    g1_affine_t *in = terms, *o = tree;
+    size_t cnt = n;
+    // two independent sums (V's, then U's) of cnt points each
+    stage_begin(ctx, KZG_B200_STAGE_MSM_TREE);
+    uint64_t levels = 0;
+    // the ping-pong target must hold 2 * ceil(cnt / 2) points: `tree` for the first level, then `terms`
+    while (cnt > 1) {
+        size_t nxt = (cnt + 1) / 2;
+        TreePolicy tp{in, o, (uint32_t)cnt, (uint32_t)nxt};
+        RC(launch_batch_add(ctx, tp, 2 * (uint64_t)nxt));
+        std::swap(in, o);
+        cnt = nxt;
+        levels++;
+    }
+    stage_end(ctx, levels);
+    k_fr_sum<<<1, 256, 0, ctx->stream>>>(sy, (uint32_t)n, sy + n);
+    k_write_partial<<<1, 32, 0, ctx->stream>>>(in, sy + n, d + o_part);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    std::vector<int32_t> st(2 * n);
+    CU(cudaMemcpyAsync(st.data(), d_st, 2 * n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(partial_out, d + o_part, 224, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    stage_collect(ctx);
+    for (size_t i = 0; i < 2 * n; i++)
+        if (st[i] != KZG_B200_OK) return KZG_B200_BAD_ARGS;
+    return KZG_B200_OK;
+}
+extern "C" int kzg_b200_verify_phase_b(kzg_b200_ctx *ctx, const uint8_t *commitments, const uint8_t *zy, const uint8_t *proofs,
+                                       size_t n, const uint8_t r[32], uint64_t first_index, uint8_t partial_out[224]) {
+    if (!ctx || !r || !partial_out || (n && (!commitments || !zy || !proofs))) return KZG_B200_BAD_ARGS;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    return verify_phase_b_locked(ctx, commitments, zy, proofs, n, r, first_index, partial_out);
+}
+
+extern "C" int kzg_b200_verify_finish(const kzg_b200_ctx *ctx, const uint8_t *partials, size_t n_partials, int *ok) {
+    if (!ctx || !ok || (n_partials && !partials)) return KZG_B200_BAD_ARGS;
+    *ok = 0;
+    return host_verify_finish(partials, n_partials, ctx->tau_prepared, ok) == 0 ? KZG_B200_OK : KZG_B200_BAD_ARGS;
+}
+
+extern "C" int kzg_b200_verify_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments,
+                                                    const uint8_t *proofs, size_t n, int *ok) {
+    if (!ctx || !ok || (n && (!blobs || !commitments || !proofs))) return KZG_B200_BAD_ARGS;
+    *ok = 0;
+    if (n == 0) { *ok = 1; return KZG_B200_OK; }  // reference src/kzg.rs:653-655
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    // n == 1: the reference takes the single-proof equation e(C - [y]G, G2) == e(proof, [tau - z]G2)
+    // (src/kzg.rs:658-660 -> :409-426); for points of G1 it holds exactly when the batch equation
+    // with r^0 = 1 does, so the same path serves both.
+    std::vector<uint8_t> zy(n * 64);
+    RC(verify_phase_a_locked(ctx, blobs, commitments, proofs, n, zy.data()));
+    uint8_t r[32], partial[224];
+    RC(kzg_b200_compute_r(ctx, commitments, zy.data(), proofs, n, r));
+    RC(verify_phase_b_locked(ctx, commitments, zy.data(), proofs, n, r, 0, partial));
+    return host_verify_finish(partial, 1, ctx->tau_prepared, ok) == 0 ? KZG_B200_OK : KZG_B200_BAD_ARGS;
+}
+
+extern "C" int kzg_b200_pairings_verify(const uint8_t a1[48], const uint8_t a2[96], const uint8_t b1[48], const uint8_t b2[96],
+                                        int *ok) {
+    if (!a1 || !a2 || !b1 || !b2 || !ok) return KZG_B200_BAD_ARGS;
+    return host_pairings_verify(a1, a2, b1, b2, ok) == 0 ? KZG_B200_OK : KZG_B200_BAD_ARGS;
+}

@@ -1,0 +1,149 @@
+"""-m gpu: verify_blob_kzg_proof / verify_blob_kzg_proof_batch through the C ABI against the
+reference's vectors, plus the two-phase (sharded) form used for multi-GPU verification."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from golden_util import golden
+from gpu_util import gpu_settings, oracle_settings, synthetic_blobs
+
+pytestmark = pytest.mark.gpu
+G = golden()
+
+
+def _kzg():
+    import kzg_rust_b200
+    return kzg_rust_b200
+
+
+def _ids(fn):
+    return [c["name"] for c in G.by_fn(fn)]
+
+
+@pytest.mark.parametrize("case", G.by_fn("verify_blob_kzg_proof"), ids=_ids("verify_blob_kzg_proof"))
+def test_verify_blob_kzg_proof_vectors(case):
+    """reference src/lib.rs:142-175."""
+    k = _kzg()
+    s = gpu_settings("mainnet", 8)
+    try:
+        blob = k.Blob.from_bytes(G.get_bytes(case["input"]["blob"]))
+        c = k.Bytes48.from_bytes(G.get_bytes(case["input"]["commitment"]))
+        p = k.Bytes48.from_bytes(G.get_bytes(case["input"]["proof"]))
+    except (k.Error, ValueError):
+        assert case["output"] is None
+        return
+    try:
+        ok = k.Kzg.verify_blob_kzg_proof(blob, c, p, s)
+    except k.Error:
+        assert case["output"] is None
+        return
+    assert ok is case["output"]
+
+
+@pytest.mark.parametrize("case", G.by_fn("verify_blob_kzg_proof_batch"), ids=_ids("verify_blob_kzg_proof_batch"))
+def test_verify_blob_kzg_proof_batch_vectors(case):
+    """reference src/lib.rs:177-203."""
+    k = _kzg()
+    s = gpu_settings("mainnet", 8)
+    try:
+        blobs = [k.Blob.from_bytes(G.get_bytes(v)) for v in case["input"]["blobs"]]
+        cs = [k.Bytes48.from_bytes(G.get_bytes(v)) for v in case["input"]["commitments"]]
+        ps = [k.Bytes48.from_bytes(G.get_bytes(v)) for v in case["input"]["proofs"]]
+    except (k.Error, ValueError):
+        assert case["output"] is None
+        return
+    try:
+        ok = k.Kzg.verify_blob_kzg_proof_batch(blobs, cs, ps, s)
+    except k.Error:
+        assert case["output"] is None
+        return
+    assert ok is case["output"]
+
+
+def _make_batch(k, s, n, seed):
+    blobs = synthetic_blobs(n, seed=seed)
+    cms, st = k.Kzg.blob_to_kzg_commitment_batch(blobs, s)
+    assert not st.any()
+    proofs, st = k.Kzg.compute_blob_kzg_proof_batch(blobs, cms, s)
+    assert not st.any()
+    return blobs, cms, proofs
+
+
+def test_config3_batch_of_6_and_negative_control():
+    """BASELINE.json config 3 at the Deneb block maximum; the oracle agrees on both outcomes."""
+    k = _kzg()
+    s = gpu_settings("mainnet", 8)
+    o = oracle_settings("mainnet")
+    blobs, cms, proofs = _make_batch(k, s, 6, 601)
+    assert k.Kzg.verify_blob_kzg_proof_batch_raw(blobs, cms, proofs, 6, s) is True
+    lists = lambda a: [a[i].tobytes() for i in range(len(a))]
+    assert o.verify_blob_kzg_proof_batch(lists(blobs), lists(cms), lists(proofs)) is True
+    bad = proofs.copy()
+    bad[[0, 5]] = bad[[5, 0]]
+    assert k.Kzg.verify_blob_kzg_proof_batch_raw(blobs, cms, bad, 6, s) is False
+    assert o.verify_blob_kzg_proof_batch(lists(blobs), lists(cms), lists(bad)) is False
+    # a single flipped blob byte changes z and y, so the proof no longer fits
+    b2 = blobs.copy()
+    b2[3, 100] ^= 1
+    assert k.Kzg.verify_blob_kzg_proof_batch_raw(b2, cms, proofs, 6, s) is False
+
+
+def test_two_phase_sharded_verify_matches_single_call():
+    """phase A per shard, one r for the whole batch, phase B per shard with the
+    shard's first index, partial sums combined by verify_finish."""
+    k = _kzg()
+    L = k.load_library()
+    s = gpu_settings("mainnet", 8)
+    n = 11
+    blobs, cms, proofs = _make_batch(k, s, n, 77)
+    for tamper in (False, True):
+        pr = proofs.copy()
+        if tamper:
+            pr[[2, 9]] = pr[[9, 2]]
+        shards = [(0, 4), (4, 5), (5, 11)]
+        zy = np.zeros((n, 64), dtype=np.uint8)
+        for lo, hi in shards:
+            rc = L.kzg_b200_verify_phase_a(s._h, blobs[lo:hi].ctypes.data, cms[lo:hi].ctypes.data, pr[lo:hi].ctypes.data,
+                                           hi - lo, zy[lo:hi].ctypes.data)
+            assert rc == 0
+        r = np.zeros(32, dtype=np.uint8)
+        assert L.kzg_b200_compute_r(s._h, cms.ctypes.data, zy.ctypes.data, pr.ctypes.data, n, r.ctypes.data) == 0
+        partials = np.zeros((len(shards), 224), dtype=np.uint8)
+        for j, (lo, hi) in enumerate(shards):
+            rc = L.kzg_b200_verify_phase_b(s._h, cms[lo:hi].ctypes.data, zy[lo:hi].ctypes.data, pr[lo:hi].ctypes.data,
+                                           hi - lo, r.ctypes.data, lo, partials[j].ctypes.data)
+            assert rc == 0
+        ok = ctypes.c_int(-1)
+        assert L.kzg_b200_verify_finish(s._h, partials.ctypes.data, len(shards), ctypes.byref(ok)) == 0
+        assert bool(ok.value) is (not tamper)
+        assert k.Kzg.verify_blob_kzg_proof_batch_raw(blobs, cms, pr, n, s) is (not tamper)
+
+
+def test_challenge_and_evaluation_match_oracle():
+    """z_i and y_i of phase A are bit-exact with compute_challenge /
+    evaluate_polynomial_in_evaluation_form of the oracle."""
+    k = _kzg()
+    L = k.load_library()
+    s = gpu_settings("mainnet", 8)
+    o = oracle_settings("mainnet")
+    blobs, cms, proofs = _make_batch(k, s, 5, 5)
+    zy = np.zeros((5, 64), dtype=np.uint8)
+    assert L.kzg_b200_verify_phase_a(s._h, blobs.ctypes.data, cms.ctypes.data, proofs.ctypes.data, 5, zy.ctypes.data) == 0
+    for i in range(5):
+        z = o.compute_challenge(blobs[i].tobytes(), cms[i].tobytes())
+        assert zy[i, :32].tobytes() == z
+        assert zy[i, 32:].tobytes() == o.evaluate_polynomial(blobs[i].tobytes(), z)
+
+
+def test_pairing_check_matches_oracle():
+    from oracle import binding as ob
+    k = _kzg()
+    L = k.load_library()
+    g1 = [G.g1_bytes[48 * i:48 * i + 48] for i in range(4)]
+    g2 = [G.g2_bytes[96 * i:96 * i + 96] for i in range(2)]
+    tau_p = ob.g1_lincomb([g1[2]], [(1337).to_bytes(32, "big")])
+    for a1, a2, b1, b2 in ((g1[2], g2[1], tau_p, g2[0]), (g1[1], g2[0], g1[0], g2[1]), (g1[3], g2[1], tau_p, g2[0])):
+        ok = ctypes.c_int(-1)
+        assert L.kzg_b200_pairings_verify(a1, a2, b1, b2, ctypes.byref(ok)) == 0
+        assert bool(ok.value) is ob.pairings_verify(a1, a2, b1, b2)
