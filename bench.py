@@ -1,0 +1,367 @@
+#!/usr/bin/env python3
+"""bench.py -- blobs/sec of the B200 blob path (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of `blob_to_kzg_commitment` over one batch of synthetic blobs
+(BASELINE.json configs[3]: 65,536 blobs; reference generator benches/kzg_benches.rs:14-23).
+Blobs are independent, so every rank processes its own batch with its own context and there is
+no data-path collective (weak scaling); the only collective is the barrier / max-reduce of the
+timings.
+
+  value      whole-job blobs/s with the blobs already resident in HBM (device entry point)
+  e2e        the same through the host-buffer C ABI call (kzg_b200_blob_to_kzg_commitment_batch):
+             pinned host blobs -> H2D -> kernels -> D2H of commitments + status, all timed
+  roofline   the MSM kernel (batch_add_kernel, all instantiations) against the measured
+             integer-multiply issue rate; per-stage device times come from CUDA events on
+             the context's stream (kzg_b200_profile_*)
+  cpu_baseline / --impl reference
+             the CPU restatement (oracle/, a port: the crate's blst path cannot be built here)
+             on the box's host cores
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+BYTES_PER_BLOB = 131072
+# BASELINE.md section 3 (fixed constants): algorithmic integer-multiply work per blob
+IMAD_PER_COMMIT = 3.24e8
+IMAD_PER_PROOF = 3.34e8
+HBM_BYTES_PER_COMMIT = 131120
+STAGES = ["digits", "msm_gather", "msm_tree", "compress", "challenge", "eval", "validate", "verify_terms"]
+
+
+def read_setup():
+    from golden_util import golden
+    g = golden()
+    return g.g1_bytes, g.g2_bytes
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for j, nm in enumerate(names) if any(r[3 + j].lower().startswith("active") for r in rows)]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].isdigit() else None,
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(rows)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of the reference's path on the host cores."""
+    if rank != 0:
+        return
+    import numpy as np
+    from gpu_util import oracle_settings, synthetic_blobs
+    cores = os.cpu_count() or 1
+    o = oracle_settings("mainnet")
+    per_step = 2 * cores
+    blobs = synthetic_blobs(per_step, seed=0xB200)
+    for _ in range(max(1, min(args.warmup, 1))):
+        o.blob_to_kzg_commitment_many(blobs[:cores], nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out, st = o.blob_to_kzg_commitment_many(blobs, nthreads=cores)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = "%d blobs per step x %d steps, one blob per thread on %d threads" % (per_step, args.steps, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "blob_to_kzg_commitment throughput", "value": value, "unit": "blobs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit Fp / 255-bit Fr integers)",
+        "data": "synthetic",
+        "config": {"workload": "mainnet blob_to_kzg_commitment, synthetic blobs (top byte of each element zero), trusted_setup.txt"},
+        "cpu_baseline": {"value": value, "unit": "blobs/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "CPU restatement (oracle/kzg_oracle.c), not blst: cargo/rustc and the blst sources are absent here"},
+        "e2e": {"value": value, "unit": "blobs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--blobs", type=int, default=int(os.environ.get("KZG_BENCH_BLOBS", 65536)), help="blobs per GPU per step")
+    ap.add_argument("--host-pool", type=int, default=8192, help="pinned host blobs reused by the end-to-end leg")
+    ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--no-proof", action="store_true", help="skip the compute_blob_kzg_proof side measurement")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import kzg_rust_b200 as k
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = k.load_library()
+    g1, g2 = read_setup()
+    t_create = time.time()
+    s = k.KzgSettings.load_trusted_setup(g1, g2, local_rank, args.window_bits)
+    t_create = time.time() - t_create
+    stream = torch.cuda.ExternalStream(L.kzg_b200_stream(s._h), device=dev)
+    B = args.blobs
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # synthetic blobs on the device (reference generator: uniform bytes, top byte of each element 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0xB200 + rank)
+    blobs = torch.empty((B, 4096, 32), dtype=torch.uint8, device=dev)
+    for lo in range(0, B, 4096):
+        hi = min(B, lo + 4096)
+        blobs[lo:hi] = torch.randint(0, 256, (hi - lo, 4096, 32), dtype=torch.uint8, device=dev, generator=gen)
+    blobs[:, :, 0] = 0
+    out = torch.zeros((B, 48), dtype=torch.uint8, device=dev)
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    proofs = torch.zeros((B, 48), dtype=torch.uint8, device=dev)
+
+    def commit_device():
+        rc = L.kzg_b200_blob_to_kzg_commitment_device(s._h, blobs.data_ptr(), B, out.data_ptr(), status.data_ptr())
+        if rc:
+            raise SystemExit("kzg_b200_blob_to_kzg_commitment_device failed: %d" % rc)
+
+    def proof_device():
+        rc = L.kzg_b200_compute_blob_kzg_proof_device(s._h, blobs.data_ptr(), out.data_ptr(), B, proofs.data_ptr(), status.data_ptr())
+        if rc:
+            raise SystemExit("kzg_b200_compute_blob_kzg_proof_device failed: %d" % rc)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        L.kzg_b200_synchronize(s._h)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = L.kzg_b200_launch_count(s._h)
+        w0 = time.time()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        L.kzg_b200_synchronize(s._h)
+        w1 = time.time()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), L.kzg_b200_launch_count(s._h) - l0, (w0, w1)
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+
+    # ---- device-resident leg (value) with per-stage timing
+    for _ in range(args.warmup):
+        commit_device()
+    L.kzg_b200_profile_enable(s._h, 1)
+    ms, launches, (w0, w1) = timed(commit_device, args.steps, 0)
+    stage_ms = (ctypes.c_double * 8)()
+    stage_ln = (ctypes.c_uint64 * 8)()
+    L.kzg_b200_profile_read(s._h, stage_ms, stage_ln)
+    L.kzg_b200_profile_enable(s._h, 0)
+    if int(status.any().item()):
+        raise SystemExit("synthetic blobs were rejected")
+    value = world * B * args.steps / (ms * 1e-3)
+    clock_summary = clocks.summary(w0, w1) if clocks else None
+
+    # ---- end-to-end leg: pinned host blobs through the host-buffer C ABI call
+    pool = min(args.host_pool, B)
+    h_blobs = torch.empty((pool, BYTES_PER_BLOB), dtype=torch.uint8, pin_memory=True)
+    h_blobs.copy_(blobs[:pool].reshape(pool, BYTES_PER_BLOB))
+    h_out = torch.empty((pool, 48), dtype=torch.uint8, pin_memory=True)
+    h_status = torch.empty(pool, dtype=torch.int32, pin_memory=True)
+    calls = (B + pool - 1) // pool
+
+    def commit_host():
+        for _ in range(calls):
+            rc = L.kzg_b200_blob_to_kzg_commitment_batch(s._h, h_blobs.data_ptr(), pool, h_out.data_ptr(), h_status.data_ptr())
+            if rc:
+                raise SystemExit("kzg_b200_blob_to_kzg_commitment_batch failed: %d" % rc)
+
+    e2e_ms, _, _ = timed(commit_host, args.steps, min(args.warmup, 1))
+    e2e_value = world * calls * pool * args.steps / (e2e_ms * 1e-3)
+    same = bool((h_out.to(dev) == out[:pool]).all().item()) and not bool(h_status.any().item())
+    if not same:
+        raise SystemExit("host-buffer and device-resident paths disagree")
+
+    # ---- compute_blob_kzg_proof side measurement (the other half of BASELINE.json's metric)
+    proof = None
+    if not args.no_proof:
+        pms, _, _ = timed(proof_device, 1, 1)
+        if int(status.any().item()):
+            raise SystemExit("proof path rejected synthetic blobs")
+        proof = {"metric": "compute_blob_kzg_proof throughput", "value": world * B / (pms * 1e-3), "unit": "blobs/s",
+                 "steps": 1, "warmup": 1, "ms_per_step": pms,
+                 "imad_roofline_frac": None}
+    # ---- verify_blob_kzg_proof_batch side measurement (BASELINE.json configs[2]: 6 and 1024 blobs),
+    # host buffers through kzg_b200_verify_blob_kzg_proof_batch, wall clock around the blocking call
+    verify = None
+    if proof is not None and rank == 0:
+        nv = min(1024, B)
+        vb = blobs[:nv].reshape(nv, BYTES_PER_BLOB).cpu().numpy()
+        vc, vp = out[:nv].cpu().numpy(), proofs[:nv].cpu().numpy()
+        verify = {}
+        for n_v, reps in ((6, 5), (nv, 2)):
+            if not k.Kzg.verify_blob_kzg_proof_batch_raw(vb[:n_v], vc[:n_v], vp[:n_v], n_v, s):
+                raise SystemExit("verify_blob_kzg_proof_batch rejected proofs made by the path itself")
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                k.Kzg.verify_blob_kzg_proof_batch_raw(vb[:n_v], vc[:n_v], vp[:n_v], n_v, s)
+            dt = (time.perf_counter() - t0) / reps
+            verify["n=%d" % n_v] = {"ms_per_call": dt * 1e3, "blobs_per_s": n_v / dt}
+        bad = vp[:6].copy()
+        bad[[0, 5]] = bad[[5, 0]]
+        verify["negative_control_rejected"] = not k.Kzg.verify_blob_kzg_proof_batch_raw(vb[:6], vc[:6], bad, 6, s)
+    if clocks:
+        clocks.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (batch_add_kernel: gather level + tree levels)
+    imad, imadw, fpmul = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    L.kzg_b200_measure_peaks(s._h, ctypes.byref(imad), ctypes.byref(imadw), ctypes.byref(fpmul))
+    peaks, peaks_kind = measured_peaks()
+    msm_ms = stage_ms[1] + stage_ms[2]
+    msm_launches = int(stage_ln[1] + stage_ln[2])
+    blobs_timed = B * args.steps
+    achieved = IMAD_PER_COMMIT * blobs_timed / (msm_ms * 1e-3) if msm_ms > 0 else 0.0
+    wn = None
+    roofline = {
+        "bound": "imad", "kernel": "batch_add_kernel (GatherPolicy + TreePolicy launches)",
+        "achieved": achieved / 1e12, "peak": imad.value / 1e12, "unit": "TIMAD/s", "frac": achieved / imad.value if imad.value else None,
+        "traffic": None,
+        "launches": msm_launches, "avg_launch_ms": msm_ms / max(1, msm_launches),
+        "algorithmic_imad_per_blob": IMAD_PER_COMMIT,
+        "peak_source": "mad.lo.u32 issue-rate micro-benchmark run in this process (kzg_b200_measure_peaks); "
+                       "MEASURED_PEAKS.json has no integer figure",
+        "wide_mac_per_s": imadw.value, "fp_mul_per_s": fpmul.value,
+        "whole_step_frac": IMAD_PER_COMMIT * value / world / imad.value if imad.value else None,
+        "hbm": {"achieved_gbs": HBM_BYTES_PER_COMMIT * value / world / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                "frac": HBM_BYTES_PER_COMMIT * value / world / 1e9 / peaks.get("hbm_gbs", 1.0), "peak_kind": peaks_kind},
+        "stage_ms_per_step": {STAGES[i]: stage_ms[i] / args.steps for i in range(8) if stage_ms[i] > 0},
+    }
+    if proof is not None and imad.value:
+        proof["imad_roofline_frac"] = IMAD_PER_PROOF * proof["value"] / world / imad.value
+
+    # ---- CPU baseline (bounded sample) + parity spot check of the GPU output against it
+    cpu = None
+    if not args.no_cpu and world == 1:
+        from gpu_util import oracle_settings
+        cores = os.cpu_count() or 1
+        o = oracle_settings("mainnet")
+        nsamp = 16 * cores
+        sample = blobs[:nsamp].reshape(nsamp, BYTES_PER_BLOB).cpu().numpy()
+        o.blob_to_kzg_commitment_many(sample[:cores], nthreads=cores)
+        t0 = time.perf_counter()
+        exp, est = o.blob_to_kzg_commitment_many(sample, nthreads=cores)
+        dt = time.perf_counter() - t0
+        got = out[:nsamp].cpu().numpy()
+        if est.any() or not np.array_equal(got, exp):
+            raise SystemExit("GPU commitments differ from the CPU oracle on the sampled blobs")
+        cpu = {"value": nsamp / dt, "unit": "blobs/s", "cores": cores, "kind": "port",
+               "sample": "first %d blobs of the batch, one blob per thread on %d threads (%.1f s)" % (nsamp, cores, dt),
+               "parity": "GPU commitments byte-equal on the sample",
+               "note": "CPU restatement (oracle/kzg_oracle.c), not blst"}
+
+    line = {
+        "metric": "blob_to_kzg_commitment throughput", "value": value, "unit": "blobs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit Fp / 255-bit Fr integers)", "data": "synthetic",
+        "config": {"workload": "mainnet blob_to_kzg_commitment, %d synthetic blobs per GPU per step (BASELINE.json configs[3]), "
+                               "trusted_setup.txt" % B,
+                   "blobs_per_gpu_per_step": B, "window_bits": s.window_bits, "sharding": "independent blobs, one context per GPU, no collective",
+                   "l2": "inputs (%.1f GiB per step) exceed L2" % (B * BYTES_PER_BLOB / 2 ** 30), "ctx_create_s": round(t_create, 2)},
+        "e2e": {"value": e2e_value, "unit": "blobs/s", "h2d_bytes_per_step": calls * pool * BYTES_PER_BLOB,
+                "d2h_bytes_per_step": calls * pool * 52, "ms_per_step": e2e_ms / args.steps,
+                "api": "kzg_b200_blob_to_kzg_commitment_batch on pinned host buffers, %d calls of %d blobs per step" % (calls, pool)},
+        "gpu_launches": int(launches),
+        "clocks": clock_summary,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "also": {"compute_blob_kzg_proof": proof, "verify_blob_kzg_proof_batch": verify},
+    }
+    print(json.dumps(line), flush=True)
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

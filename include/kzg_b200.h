@@ -61,8 +61,9 @@ typedef struct kzg_b200_ctx kzg_b200_ctx;
  *   g2_monomial: n2 x 96 B compressed G2 points; n2 must be 65
  *   n1:          FIELD_ELEMENTS_PER_BLOB of the preset: 4096 (kzg_mainnet) or 4 (kzg_minimal)
  *   device:      CUDA device ordinal
- *   window_bits: signed-digit window of the precomputed table, 0 = pick the largest that
- *                fits the device's free memory (15 on a 180 GB B200, 102 GiB of table)
+ *   window_bits: signed-digit window c of the precomputed table (n1 x 2^(c-1) affine points of
+ *                96 B), 2..20; 0 = pick the largest that fits the device's free memory
+ *                (19 on an empty 180 GB B200: 14 windows, 103 GB of table; 18: 51.5 GB)
  */
 int kzg_b200_ctx_create(const uint8_t *g1_lagrange, size_t n1, const uint8_t *g2_monomial, size_t n2,
                         int device, int window_bits, kzg_b200_ctx **out);

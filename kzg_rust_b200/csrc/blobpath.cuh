@@ -64,7 +64,7 @@ inline int msm_num_windows(int c) {
 
 // Signed c-bit digits of a canonical scalar s < r:  s = sum_j d_j 2^(c j), |d_j| <= 2^(c-1),
 // W = msm_num_windows(c) so the top window never carries out.  Digit j goes to out[j*stride].
-KZG_HD void recode_signed(const fr_t &s, int c, int W, int16_t *out, uint64_t stride) {
+KZG_HD void recode_signed(const fr_t &s, int c, int W, int32_t *out, uint64_t stride) {
     const uint32_t mask = (1u << c) - 1u, half = 1u << (c - 1);
     uint32_t carry = 0;
 #pragma unroll 1
@@ -76,13 +76,13 @@ KZG_HD void recode_signed(const fr_t &s, int c, int W, int16_t *out, uint64_t st
         v += carry;
         int d;
         if (v > half) { d = (int)v - (int)(1u << c); carry = 1; } else { d = (int)v; carry = 0; }
-        out[(uint64_t)j * stride] = (int16_t)d;
+        out[(uint64_t)j * stride] = d;
     }
 }
 
 // One blob element: range check + digits.  Non-canonical elements mark the blob BADARGS
 // (reference src/utils.rs:266-270) and contribute zero digits.
-KZG_HD void blob_digits_thread(const uint8_t *blobs, uint64_t e, int n, int c, int W, int16_t *digits, int *status) {
+KZG_HD void blob_digits_thread(const uint8_t *blobs, uint64_t e, int n, int c, int W, int32_t *digits, int *status) {
     uint64_t b = e / (uint64_t)n;
     uint32_t i = (uint32_t)(e - b * n);
     fr_t s;
@@ -98,7 +98,7 @@ KZG_HD void blob_digits_thread(const uint8_t *blobs, uint64_t e, int n, int c, i
     recode_signed(s, c, W, digits + (b * W) * (uint64_t)n + i, (uint64_t)n);
 }
 // Same, from an Fr element in Montgomery form (the quotient polynomial of a proof).
-KZG_HD void fr_digits_thread(const fr_t *evals, uint64_t e, int n, int c, int W, int16_t *digits) {
+KZG_HD void fr_digits_thread(const fr_t *evals, uint64_t e, int n, int c, int W, int32_t *digits) {
     uint64_t b = e / (uint64_t)n;
     uint32_t i = (uint32_t)(e - b * n);
     fr_t s;
@@ -106,19 +106,19 @@ KZG_HD void fr_digits_thread(const fr_t *evals, uint64_t e, int n, int c, int W,
     recode_signed(s, c, W, digits + (b * W) * (uint64_t)n + i, (uint64_t)n);
 }
 
-// table[(j*n+i)*D + 0] = 2^(c j) G_i, from the previous window's base (thread i walks j).
-KZG_HD void window_base_thread(g1_affine_t *table, uint32_t i, int n, int c, int W, uint32_t D) {
+// Horner pass over the W window sums of one blob: sum_j 2^(c j) S_j, S_j affine (possibly
+// infinity) at sums[j].  (W-1)(c doublings + 1 mixed addition) in Jacobian coordinates.
+KZG_HD void horner_thread(g1_affine_t &out, const g1_affine_t *sums, int c, int W) {
+    g1_jac_t acc;
+    g1j_from_affine(acc, sums[W - 1]);
 #pragma unroll 1
-    for (int j = 1; j < W; j++) {
-        g1_affine_t prev = table[((uint64_t)(j - 1) * n + i) * D];
-        g1_jac_t t;
-        g1j_from_affine(t, prev);
+    for (int j = W - 2; j >= 0; j--) {
 #pragma unroll 1
-        for (int k = 0; k < c; k++) g1j_dbl(t, t);
-        g1_affine_t a;
-        g1j_to_affine(a, t);
-        table[((uint64_t)j * n + i) * D] = a;
+        for (int k = 0; k < c; k++) g1j_dbl(acc, acc);
+        g1_affine_t s = sums[j];
+        if (!g1a_is_inf(s)) g1j_add_affine(acc, acc, s.x, s.y);
     }
+    g1j_to_affine(out, acc);
 }
 
 // Setup / validation: one compressed point -> affine Montgomery (+ optional subgroup check,

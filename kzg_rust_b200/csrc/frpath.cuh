@@ -158,7 +158,7 @@ __global__ void k_load_scalars(const uint8_t *__restrict__ in, uint32_t count, f
 template <bool QUOT>
 __global__ void __launch_bounds__(KZG_EVAL_THREADS) k_eval_quotient(
     const uint8_t *__restrict__ blobs, const fr_t *__restrict__ z_canon, const fr_t *__restrict__ roots, int n,
-    fr_t *__restrict__ inv, fr_t *__restrict__ poly, uint8_t *__restrict__ zy_out, int16_t *__restrict__ digits, int c,
+    fr_t *__restrict__ inv, fr_t *__restrict__ poly, uint8_t *__restrict__ zy_out, int32_t *__restrict__ digits, int c,
     int W, int32_t *status) {
     constexpr int T = KZG_EVAL_THREADS;
     __shared__ fr_t sh_pre[2][T];
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(KZG_EVAL_THREADS) k_eval_quotient(
     __syncthreads();
     if (!QUOT) return;
     const fr_t y = sh_val[1];
-    int16_t *bdig = digits + (size_t)b * W * n;
+    int32_t *bdig = digits + (size_t)b * W * n;
     fe_set_zero(acc);
 #pragma unroll 1
     for (int i = tid; i < n; i += T) {

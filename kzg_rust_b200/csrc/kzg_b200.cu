@@ -42,15 +42,16 @@ struct kzg_b200_ctx {
     int n = 0;        // FIELD_ELEMENTS_PER_BLOB
     int c = 0;        // window bits
     int W = 0;        // windows
-    uint32_t D = 0;   // table entries per (window, point): 2^(c-1)
+    uint32_t D = 0;   // table entries per point: 2^(c-1)
     int sms = 0;
-    int max_k = 512;  // additions per thread per inversion
+    int max_k = 4096; // additions per thread per batch (one shared inversion per block and batch)
+    int add_blocks = 3;  // resident blocks per SM of the addition kernel (KZG_B200_ADD_BLOCKS)
     g1_affine_t *d_table = nullptr;
     fr_t *d_roots = nullptr;       // roots of unity, Montgomery form, bit-reversed (src/kzg.rs:764-799)
     uint8_t g2_tau[96];            // [tau]G2 = g2_values[1]
     // workspace for one chunk of blobs
     size_t chunk = 0;
-    int16_t *d_digits = nullptr;
+    int32_t *d_digits = nullptr;
     g1_affine_t *d_buf_a = nullptr, *d_buf_b = nullptr;
     fp_t *d_scratch = nullptr;
     size_t scratch_elems = 0;
@@ -120,30 +121,29 @@ __global__ void k_place_bases(const g1_affine_t *decoded, g1_affine_t *table, ui
     for (uint32_t o = n; o > 1; o >>= 1) { r = (r << 1) | (v & 1); v >>= 1; }
     table[(uint64_t)i * D] = decoded[r];
 }
-__global__ void k_window_bases(g1_affine_t *table, int n, int c, int W, uint32_t D) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (uint32_t)n) return;
-    window_base_thread(table, i, n, c, W, D);
-}
-__global__ void k_blob_digits(const uint8_t *blobs, uint64_t total, int n, int c, int W, int16_t *digits,
+__global__ void k_blob_digits(const uint8_t *blobs, uint64_t total, int n, int c, int W, int32_t *digits,
                               int32_t *status) {
     uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     blob_digits_thread(blobs, e, n, c, W, digits, status);
 }
-__global__ void k_fr_digits(const fr_t *evals, uint64_t total, int n, int c, int W, int16_t *digits) {
+__global__ void k_fr_digits(const fr_t *evals, uint64_t total, int n, int c, int W, int32_t *digits) {
     uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     fr_digits_thread(evals, e, n, c, W, digits);
 }
-__global__ void k_compress(const g1_affine_t *pts, const int32_t *status, uint8_t *out, uint32_t count) {
+// window sums of blob i (W affine points) -> Horner -> 48-byte compressed point
+__global__ void __launch_bounds__(64) k_horner_compress(const g1_affine_t *sums, int c, int W, const int32_t *status, uint8_t *out,
+                                                        uint32_t count) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     uint8_t buf[48];
     if (status && status[i] != KZG_OK) {
         for (int k = 0; k < 48; k++) buf[k] = 0;
     } else {
-        g1a_compress(buf, pts[i]);
+        g1_affine_t p;
+        horner_thread(p, sums + (size_t)i * W, c, W);
+        g1a_compress(buf, p);
     }
     uint32_t *o = reinterpret_cast<uint32_t *>(out + 48ull * i);
 #pragma unroll
@@ -233,7 +233,7 @@ template <class Policy>
 static int launch_batch_add(kzg_b200_ctx *ctx, const Policy &pol, uint64_t total) {
     if (total == 0) return KZG_B200_OK;
     const unsigned tpb = KZG_ADD_THREADS;
-    const uint64_t t_max = (uint64_t)ctx->sms * KZG_ADD_MIN_BLOCKS * tpb;
+    const uint64_t t_max = (uint64_t)ctx->sms * ctx->add_blocks * tpb;
     uint64_t T;
     int k;
     if (total <= t_max) {
@@ -245,25 +245,29 @@ static int launch_batch_add(kzg_b200_ctx *ctx, const Policy &pol, uint64_t total
         k = (int)std::min<uint64_t>(need, (uint64_t)ctx->max_k);
     }
     RC(ensure_scratch(ctx, (size_t)(T * k)));
-    batch_add_kernel<Policy><<<(unsigned)(T / tpb), tpb, 0, ctx->stream>>>(pol, total, ctx->d_scratch, k);
+    if (ctx->add_blocks >= 4)
+        batch_add_kernel<Policy, 4><<<(unsigned)(T / tpb), tpb, 0, ctx->stream>>>(pol, total, ctx->d_scratch, k);
+    else
+        batch_add_kernel<Policy, 3><<<(unsigned)(T / tpb), tpb, 0, ctx->stream>>>(pol, total, ctx->d_scratch, k);
     ctx->launches++;
     CU(cudaGetLastError());
     return KZG_B200_OK;
 }
 
-// sum of the W*n table entries selected by d_digits, for `count` blobs -> result[b] in *out
+// the W window sums (4096 table entries each, selected by d_digits) of `count` blobs:
+// (*out)[b*W + j] = S_j of blob b
 static int run_msm(kzg_b200_ctx *ctx, size_t count, const g1_affine_t **out) {
     uint32_t per_blob = (uint32_t)ctx->W * ctx->n, cnt = per_blob / 2;
-    GatherPolicy gp{ctx->d_table, ctx->d_digits, ctx->d_buf_a, per_blob, ctx->D};
+    GatherPolicy gp{ctx->d_table, ctx->d_digits, ctx->d_buf_a, per_blob, (uint32_t)ctx->n - 1, ctx->D};
     stage_begin(ctx, KZG_B200_STAGE_MSM_GATHER);
     RC(launch_batch_add(ctx, gp, (uint64_t)count * cnt));
     stage_end(ctx, 1);
     g1_affine_t *in = ctx->d_buf_a, *o = ctx->d_buf_b;
     stage_begin(ctx, KZG_B200_STAGE_MSM_TREE);
     uint64_t levels = 0;
-    while (cnt > 1) {
-        uint32_t nxt = (cnt + 1) / 2;
-        TreePolicy tp{in, o, cnt, nxt};
+    while (cnt > (uint32_t)ctx->W) {  // n is a power of two: pairs never straddle two windows
+        uint32_t nxt = cnt / 2;
+        PairPolicy tp{in, o};
         RC(launch_batch_add(ctx, tp, (uint64_t)count * nxt));
         std::swap(in, o);
         cnt = nxt;
@@ -277,7 +281,7 @@ static int run_msm(kzg_b200_ctx *ctx, size_t count, const g1_affine_t **out) {
 // ------------------------------------------------------------------ workspace
 static size_t per_blob_workspace(const kzg_b200_ctx *ctx) {
     size_t wn = (size_t)ctx->W * ctx->n;
-    return wn * 2 /*digits*/ + wn / 2 * sizeof(g1_affine_t) + (wn / 4 + 1) * sizeof(g1_affine_t) +
+    return wn * 4 /*digits*/ + wn / 2 * sizeof(g1_affine_t) + (wn / 4 + 1) * sizeof(g1_affine_t) +
            (size_t)ctx->n * 32 /*stage in*/ + 2 * (size_t)ctx->n * sizeof(fr_t) /*poly, inv*/ + 96 * 2 + 64 + sizeof(fr_t) +
            2 * sizeof(g1_affine_t) + 4;
 }
@@ -292,7 +296,7 @@ static void free_workspace(kzg_b200_ctx *ctx) {
 static int alloc_workspace(kzg_b200_ctx *ctx, size_t chunk) {
     free_workspace(ctx);
     size_t wn = (size_t)ctx->W * ctx->n;
-    CU(cudaMalloc(&ctx->d_digits, chunk * wn * sizeof(int16_t)));
+    CU(cudaMalloc(&ctx->d_digits, chunk * wn * sizeof(int32_t)));
     CU(cudaMalloc(&ctx->d_buf_a, chunk * (wn / 2) * sizeof(g1_affine_t)));
     CU(cudaMalloc(&ctx->d_buf_b, chunk * (wn / 4 + 1) * sizeof(g1_affine_t)));
     CU(cudaMalloc(&ctx->d_stage_in, chunk * (size_t)ctx->n * 32));
@@ -333,12 +337,11 @@ static int build_table(kzg_b200_ctx *ctx, const uint8_t *g1_bytes) {
     for (int i = 0; i < n; i++)
         if (st[i] != 0) { cudaFree(d_bytes); cudaFree(d_dec); cudaFree(d_st); return KZG_B200_BAD_ARGS; }
     k_place_bases<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(d_dec, ctx->d_table, n, ctx->D);
-    k_window_bases<<<blocks_for(n, 32), 32, 0, ctx->stream>>>(ctx->d_table, n, ctx->c, ctx->W, ctx->D);
-    ctx->launches += 2;
+    ctx->launches += 1;
     CU(cudaGetLastError());
     for (int L = 0; L + 1 < ctx->c; L++) {
         TableLevelPolicy pol{ctx->d_table, ctx->D, (uint32_t)L};
-        RC(launch_batch_add(ctx, pol, ((uint64_t)ctx->W * n) << L));
+        RC(launch_batch_add(ctx, pol, (uint64_t)n << L));
     }
     CU(cudaStreamSynchronize(ctx->stream));
     cudaFree(d_bytes); cudaFree(d_dec); cudaFree(d_st);
@@ -369,23 +372,25 @@ extern "C" int kzg_b200_ctx_create(const uint8_t *g1_lagrange, size_t n1, const 
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return KZG_B200_CUDA_ERROR; }
     ctx->sms = prop.multiProcessorCount;
-    ctx->max_k = env_int("KZG_B200_BATCH_K", 512);
+    ctx->max_k = env_int("KZG_B200_BATCH_K", 4096);
+    ctx->add_blocks = env_int("KZG_B200_ADD_BLOCKS", 3) >= 4 ? 4 : 3;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KZG_B200_CUDA_ERROR; }
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     int c = window_bits > 0 ? window_bits : env_int("KZG_B200_WINDOW_BITS", 0);
     if (c <= 0) {
         // largest window whose table leaves room for a 4096-blob workspace and 16 GiB of caller data
-        for (c = 15; c > 2; c--) {
-            size_t tbl = (size_t)msm_num_windows(c) * n1 * ((size_t)1 << (c - 1)) * sizeof(g1_affine_t);
-            if (tbl + ((size_t)40 << 30) <= free_b) break;
+        // (19 on an empty 180 GB B200: 14 windows, 103 GB of table)
+        for (c = 19; c > 2; c--) {
+            size_t tbl = n1 * ((size_t)1 << (c - 1)) * sizeof(g1_affine_t);
+            if (tbl + ((size_t)44 << 30) <= free_b) break;
         }
     }
-    if (c < 2 || c > 15) { kzg_b200_ctx_destroy(ctx); return KZG_B200_BAD_ARGS; }
+    if (c < 2 || c > 20) { kzg_b200_ctx_destroy(ctx); return KZG_B200_BAD_ARGS; }
     ctx->c = c;
     ctx->W = msm_num_windows(c);
     ctx->D = 1u << (c - 1);
-    size_t tbl_bytes = (size_t)ctx->W * n1 * ctx->D * sizeof(g1_affine_t);
+    size_t tbl_bytes = n1 * (size_t)ctx->D * sizeof(g1_affine_t);
     if (cudaMalloc(&ctx->d_table, tbl_bytes) != cudaSuccess) { kzg_b200_ctx_destroy(ctx); return KZG_B200_CUDA_ERROR; }
     int rc = build_table(ctx, g1_lagrange);
     if (rc != KZG_B200_OK) { kzg_b200_ctx_destroy(ctx); return rc; }
@@ -499,7 +504,7 @@ static int commit_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, size_t count,
     const g1_affine_t *res = nullptr;
     RC(run_msm(ctx, count, &res));
     stage_begin(ctx, KZG_B200_STAGE_COMPRESS);
-    k_compress<<<blocks_for(count, 64), 64, 0, ctx->stream>>>(res, d_status, d_out, (uint32_t)count);
+    k_horner_compress<<<blocks_for(count, 64), 64, 0, ctx->stream>>>(res, ctx->c, ctx->W, d_status, d_out, (uint32_t)count);
     stage_end(ctx, 1);
     ctx->launches++;
     CU(cudaGetLastError());

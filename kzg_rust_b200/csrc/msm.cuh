@@ -4,15 +4,17 @@
 //
 //   * The 4096 Lagrange-basis points never change, so every multiple a signed c-bit digit
 //     can ask for is precomputed once per context and kept in HBM:
-//         table[(j*n + i)*D + (d-1)] = d * 2^(c*j) * G_i,   d = 1 .. D = 2^(c-1)
-//     (c = 15: 17 windows, 102 GiB of the 180 GB).  A commitment is then just the sum of
-//     W*n table entries -- no buckets, no bucket reduction, no doublings.
-//   * That sum is a binary tree of *affine* additions.  Each level is one launch of
+//         table[i*D + (d-1)] = d * G_i,   d = 1 .. D = 2^(c-1)
+//     (c = 18: 51.5 GB, c = 19: 103 GB of the 180 GB).  With s_i = sum_j d_ij 2^(c j),
+//         sum_i s_i G_i = sum_j 2^(c j) S_j,   S_j = sum_i d_ij G_i  (4096 table entries)
+//     so a commitment is W = ceil(255/c) sums of 4096 table entries -- no buckets and no
+//     bucket reduction -- followed by one short Horner pass (W-1 times c doublings + 1 add).
+//   * Each S_j is a binary tree of *affine* additions.  Each level is one launch of
 //     batch_add_kernel; a thread takes k independent additions, multiplies their
-//     denominators together, inverts once (Montgomery's trick) and unwinds: 5 mul + 1 sqr
-//     per addition plus an inversion amortised over k.
+//     denominators together, the warp inverts once (Montgomery's trick across k x 32
+//     additions) and every thread unwinds: 5 mul + 1 sqr per addition.
 //   * All special cases of the group law are handled exactly (see g1.cuh), because the
-//     reference's own vectors hit them: the all-zero blob sums 69,632 infinities.
+//     reference's own vectors hit them: the all-zero blob sums 61,440 infinities.
 #pragma once
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
@@ -49,7 +51,20 @@ KZG_HD void st_fp(fp_t *p, const fp_t &r) {
 // A policy maps the flat addition index g to two source points (nullptr = infinity, with
 // an optional negation of y) and one destination.
 
-// Level >= 1 of the tree: out[b][t] = in[b][2t] + in[b][2t+1]
+// Level >= 1 of the tree when every group has an even number of points (always true for the
+// window sums: n is a power of two): out[g] = in[2g] + in[2g+1], no index arithmetic.
+struct PairPolicy {
+    const g1_affine_t *in;
+    g1_affine_t *out;
+    KZG_HD const g1_affine_t *src(uint64_t g, int which, bool &neg) const {
+        neg = false;
+        return in + 2 * g + which;
+    }
+    KZG_HD g1_affine_t *dst(uint64_t g) const { return out + g; }
+};
+
+// General form (odd group sizes; used by the small sums of batch verification):
+// out[b][t] = in[b][2t] + in[b][2t+1]
 struct TreePolicy {
     const g1_affine_t *in;
     g1_affine_t *out;
@@ -65,27 +80,28 @@ struct TreePolicy {
 };
 
 // Level 0: operands are table entries selected by the signed digits of the scalars.
-//   digits[(b*W + j)*n + i]  (int16, |d| <= D)
+//   digits[(b*W + j)*n + i]  (int32, |d| <= D); n is a power of two
 struct GatherPolicy {
     const g1_affine_t *table;
-    const int16_t *digits;
+    const int32_t *digits;
     g1_affine_t *out;
     uint32_t per_blob;  // W*n
+    uint32_t n_mask;    // n - 1
     uint32_t D;
+    // operand `which` of addition g is element 2g + which of the flat (blob, window, point)
+    // digit array; per_blob is a multiple of n, so the point index is its low bits
     KZG_HD const g1_affine_t *src(uint64_t g, int which, bool &neg) const {
-        uint32_t half = per_blob >> 1;
-        uint64_t b = g / half;
-        uint32_t e = 2 * (uint32_t)(g - b * half) + which;
-        int d = digits[b * per_blob + e];
+        uint64_t idx = 2 * g + which;
+        int d = digits[idx];
         neg = d < 0;
         if (d == 0) return nullptr;
         uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
-        return table + ((uint64_t)e * D + (mag - 1));
+        return table + ((uint64_t)((uint32_t)idx & n_mask) * D + (mag - 1));
     }
     KZG_HD g1_affine_t *dst(uint64_t g) const { return out + g; }
 };
 
-// Table construction, level L: for every slice s (= j*n + i) and d in (2^L, 2^(L+1)]:
+// Table construction, level L: for every point s (= i) and d in (2^L, 2^(L+1)]:
 //   table[s][d] = table[s][d >> 1] + table[s][(d + 1) >> 1]
 struct TableLevelPolicy {
     g1_affine_t *table;
@@ -133,6 +149,66 @@ KZG_HD void load_y(const Policy &pol, uint64_t g, int which, fp_t &y) {
 // ------------------------------------------------------------------ the hot kernel
 // total additions, spread as g = base + j*T + tid (j < k) so neighbouring threads touch
 // neighbouring memory.  scratch holds T*k prefix products (48 B each).
+// One field inversion per thread block instead of one per thread.  An inversion is 580
+// dependent multiplications; executed by every thread it costs a warp as many issue slots as
+// ~100 additions.  Instead the running products of the block's threads are combined: shuffle
+// scans give every lane the inclusive prefix and suffix products inside its warp (5 steps
+// each), the warp totals go through shared memory, warp 0 inverts the block total while the
+// other warps wait at the barrier (the other resident blocks keep the multiplier busy), and
+// thread t recovers 1/acc_t = 1/total * (product of the other warps' totals) * prefix_{t-1}
+// * suffix_{t+1}.  About 17 extra multiplications per thread buy an inversion shared by
+// 128 k additions; this is what keeps the short launches at the bottom of the addition tree
+// (few additions per thread) efficient.
+#if defined(__CUDA_ARCH__)
+KZG_D fp_t shfl_up_fp(const fp_t &v, int d) {
+    fp_t r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = __shfl_up_sync(0xffffffffu, v.l[i], d);
+    return r;
+}
+KZG_D fp_t shfl_down_fp(const fp_t &v, int d) {
+    fp_t r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = __shfl_down_sync(0xffffffffu, v.l[i], d);
+    return r;
+}
+// all threads of the block must call this the same number of times (it has barriers)
+KZG_D void shared_inverse(fp_t &inv, const fp_t &acc) {
+    __shared__ fp_t sh_tot[32];
+    __shared__ fp_t sh_inv;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    fp_t pre = acc, suf = acc;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        fp_t t = shfl_up_fp(pre, d), u = shfl_down_fp(suf, d);
+        if (lane >= d) fe_mul(pre, pre, t);
+        if (lane + d < 32) fe_mul(suf, suf, u);
+    }
+    if (lane == 31) sh_tot[warp] = pre;
+    __syncthreads();
+    if (warp == 0) {
+        fp_t total = sh_tot[0];
+#pragma unroll 1
+        for (int w = 1; w < nwarps; w++) fe_mul(total, total, sh_tot[w]);
+        fp_t tinv;
+        fp_inv(tinv, total);
+        if (lane == 0) sh_inv = tinv;
+    }
+    __syncthreads();
+    fp_t r = sh_inv;
+#pragma unroll 1
+    for (int w = 0; w < nwarps; w++)
+        if (w != warp) fe_mul(r, r, sh_tot[w]);
+    fp_t pe = shfl_up_fp(pre, 1), se = shfl_down_fp(suf, 1);
+    if (lane > 0) fe_mul(r, r, pe);
+    if (lane < 31) fe_mul(r, r, se);
+    inv = r;
+    __syncthreads();  // sh_tot / sh_inv are reused by the next batch
+}
+#else
+KZG_HD void shared_inverse(fp_t &inv, const fp_t &acc) { fp_inv(inv, acc); }
+#endif
+
 #ifndef KZG_ADD_THREADS
 #define KZG_ADD_THREADS 128
 #endif
@@ -140,40 +216,60 @@ KZG_HD void load_y(const Policy &pol, uint64_t g, int which, fp_t &y) {
 #define KZG_ADD_MIN_BLOCKS 3
 #endif
 // One thread's share; a plain function so a CPU test can walk it thread by thread.
+// Both passes are software-pipelined: the operands of the next addition are requested before
+// the multiplications of the current one, so the (random, for the gather level) HBM
+// latency hides behind ~1300 pipe cycles of field multiplication even at 12 warps per SM.
 template <class Policy>
 KZG_HD void batch_add_thread(const Policy &pol, uint64_t total, fp_t *scratch, int k, uint64_t T, uint64_t tid) {
     for (uint64_t base = 0; base < total; base += T * (uint64_t)k) {
         // pass 1: running product of the denominators
         fp_t acc = fe_one<FpParams>();
         int cnt = 0;
+        fp_t nx1, nx2;
+        {
+            uint64_t g = base + tid;
+            if (g < total) { load_x(pol, g, 0, nx1); load_x(pol, g, 1, nx2); }
+        }
 #pragma unroll 1
         for (int j = 0; j < k; j++) {
             uint64_t g = base + (uint64_t)j * T + tid;
             if (g >= total) break;
-            fp_t x1, x2, den;
-            load_x(pol, g, 0, x1);
-            load_x(pol, g, 1, x2);
+            fp_t x1 = nx1, x2 = nx2, den;
+            uint64_t gn = g + T;
+            if (j + 1 < k && gn < total) { load_x(pol, gn, 0, nx1); load_x(pol, gn, 1, nx2); }
             add_denominator(den, x1, x2, [&](fp_t &y) { load_y(pol, g, 0, y); }, [&](fp_t &y) { load_y(pol, g, 1, y); });
             st_fp(scratch + (uint64_t)j * T + tid, acc);
             fe_mul(acc, acc, den);
             cnt++;
         }
-        if (cnt == 0) continue;
+        // every lane of the warp takes part (idle lanes contribute acc = 1)
         fp_t inv;
-        fp_inv(inv, acc);
+        shared_inverse(inv, acc);
         // pass 2: unwind
+        fp_t npre;
+        if (cnt > 0) {
+            uint64_t g = base + (uint64_t)(cnt - 1) * T + tid;
+            load_x(pol, g, 0, nx1);
+            load_x(pol, g, 1, nx2);
+            ld_fp(npre, scratch + (uint64_t)(cnt - 1) * T + tid);
+        }
 #pragma unroll 1
         for (int j = cnt - 1; j >= 0; j--) {
             uint64_t g = base + (uint64_t)j * T + tid;
             g1_affine_t p1, p2, r;
-            load_x(pol, g, 0, p1.x);
-            load_x(pol, g, 1, p2.x);
+            p1.x = nx1;
+            p2.x = nx2;
+            fp_t pre = npre;
             load_y(pol, g, 0, p1.y);
             load_y(pol, g, 1, p2.y);
+            if (j > 0) {
+                load_x(pol, g - T, 0, nx1);
+                load_x(pol, g - T, 1, nx2);
+                ld_fp(npre, scratch + (uint64_t)(j - 1) * T + tid);
+            }
             fp_t den;
             int kind = add_denominator(den, p1.x, p2.x, [&](fp_t &y) { y = p1.y; }, [&](fp_t &y) { y = p2.y; });
-            fp_t pre, inv_j;
-            ld_fp(pre, scratch + (uint64_t)j * T + tid);
+            fp_t inv_j;
             fe_mul(inv_j, inv, pre);
             fe_mul(inv, inv, den);
             add_finish(r, kind, p1, p2, inv_j);
@@ -184,8 +280,10 @@ KZG_HD void batch_add_thread(const Policy &pol, uint64_t total, fp_t *scratch, i
     }
 }
 #if defined(__CUDACC__)
-template <class Policy>
-__global__ void __launch_bounds__(KZG_ADD_THREADS, KZG_ADD_MIN_BLOCKS)
+// MINB = resident blocks per SM the register allocation is tuned for (3: 168 registers, no
+// spills; 4: 128 registers, a few spilled words)
+template <class Policy, int MINB>
+__global__ void __launch_bounds__(KZG_ADD_THREADS, MINB)
 batch_add_kernel(Policy pol, uint64_t total, fp_t *__restrict__ scratch, int k) {
     batch_add_thread(pol, total, scratch, k, (uint64_t)gridDim.x * blockDim.x,
                      (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);

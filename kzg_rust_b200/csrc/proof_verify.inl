@@ -38,7 +38,7 @@ static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t 
     const g1_affine_t *res = nullptr;
     RC(run_msm(ctx, count, &res));
     stage_begin(ctx, KZG_B200_STAGE_COMPRESS);
-    k_compress<<<blocks_for(count, 64), 64, 0, ctx->stream>>>(res, d_status, d_proofs, (uint32_t)count);
+    k_horner_compress<<<blocks_for(count, 64), 64, 0, ctx->stream>>>(res, ctx->c, ctx->W, d_status, d_proofs, (uint32_t)count);
     stage_end(ctx, 1);
     ctx->launches++;
     CU(cudaGetLastError());

@@ -94,6 +94,8 @@ def load_library():
     L.kzg_b200_stream.restype = vp
     L.kzg_b200_launch_count.argtypes = [vp]
     L.kzg_b200_launch_count.restype = ctypes.c_uint64
+    L.kzg_b200_profile_enable.argtypes = [vp, ci]
+    L.kzg_b200_profile_read.argtypes = [vp, vp, vp]
     L.kzg_b200_pairings_verify.argtypes = [cp, cp, cp, cp, pci]
     L.kzg_b200_measure_peaks.argtypes = [vp] + [ctypes.POINTER(ctypes.c_double)] * 3
     _lib = L

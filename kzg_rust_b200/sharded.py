@@ -1,0 +1,128 @@
+"""Blob batches sharded over the GPUs of one box: one process (rank) and one context per GPU.
+
+Blobs are independent, so commitments and proofs need no exchange at all: every rank runs the
+batched entry point on its contiguous range.  Batch verification (reference
+verify_blob_kzg_proof_batch, src/kzg.rs:637-693) has one exchange step, because the random
+challenge r hashes every blob's (C_i, z_i, y_i, proof_i) (compute_r_powers,
+src/utils.rs:426-474):
+
+    phase A (local)   validate, z_i, y_i                           kzg_b200_verify_phase_a
+    exchange 1        all_gather of the 160-byte records
+    r                 one sequential SHA-256 over all records      kzg_b200_compute_r
+    phase B (local)   partial sums with r^(first + i)              kzg_b200_verify_phase_b
+    exchange 2        all_gather of one 224-byte partial per rank
+    finish            add the partials, one pairing check (host)   kzg_b200_verify_finish
+
+The payloads are a few hundred bytes per rank, so the collective is plain
+`torch.distributed.all_gather` (NCCL between GPUs, gloo in the CPU tests); there is no tile
+stream to fuse with it.  The arithmetic is behind a small backend interface so the driver can
+be exercised without a GPU (tests/test_multi_gpu.py); `CudaBackend` is the product path.
+"""
+import ctypes
+
+import numpy as np
+
+from . import kzg as _k
+
+
+def shard_range(n, rank, world):
+    """Contiguous, balanced ranges: the first n % world ranks get one blob more."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class CudaBackend:
+    """The four calls of the two-phase protocol on one context (one GPU)."""
+
+    def __init__(self, settings):
+        self.s = settings
+        self.L = _k.load_library()
+
+    def phase_a(self, blobs, commitments, proofs):
+        n = len(commitments) // 48
+        zy = np.zeros((n, 64), dtype=np.uint8)
+        rc = self.L.kzg_b200_verify_phase_a(self.s._h, blobs.ctypes.data, commitments.ctypes.data, proofs.ctypes.data, n,
+                                            zy.ctypes.data)
+        return rc, zy.reshape(-1)
+
+    def compute_r(self, commitments, zy, proofs):
+        r = np.zeros(32, dtype=np.uint8)
+        rc = self.L.kzg_b200_compute_r(self.s._h, commitments.ctypes.data, zy.ctypes.data, proofs.ctypes.data,
+                                       len(commitments) // 48, r.ctypes.data)
+        if rc:
+            _k._raise(rc, "compute_r")
+        return r
+
+    def phase_b(self, commitments, zy, proofs, r, first_index):
+        part = np.zeros(224, dtype=np.uint8)
+        rc = self.L.kzg_b200_verify_phase_b(self.s._h, commitments.ctypes.data, zy.ctypes.data, proofs.ctypes.data,
+                                            len(commitments) // 48, r.ctypes.data, first_index, part.ctypes.data)
+        return rc, part
+
+    def finish(self, partials):
+        ok = ctypes.c_int(0)
+        rc = self.L.kzg_b200_verify_finish(self.s._h, partials.ctypes.data, len(partials) // 224, ctypes.byref(ok))
+        if rc:
+            _k._raise(rc, "verify_finish")
+        return bool(ok.value)
+
+
+def _u8(x):
+    return np.ascontiguousarray(np.frombuffer(x, dtype=np.uint8) if isinstance(x, (bytes, bytearray)) else x.reshape(-1).view(np.uint8))
+
+
+def _all_gather_bytes(local, sizes, device):
+    """all_gather of variable-length byte arrays (sizes known on every rank)."""
+    import torch
+    import torch.distributed as dist
+    width = max(max(sizes), 1)
+    buf = torch.zeros(width, dtype=torch.uint8)
+    buf[:local.size] = torch.from_numpy(local.copy()) if local.size else buf[:0]
+    buf = buf.to(device)
+    outs = [torch.empty(width, dtype=torch.uint8, device=device) for _ in sizes]
+    dist.all_gather(outs, buf)
+    return np.concatenate([o.cpu().numpy()[:sz] for o, sz in zip(outs, sizes)]) if sizes else np.zeros(0, np.uint8)
+
+
+def verify_blob_kzg_proof_batch_sharded(backend, blobs, commitments, proofs, n_total, device="cpu"):
+    """Every rank passes ITS contiguous shard (shard_range(n_total, rank, world)) and gets the
+    verdict for the whole batch.  Raises BadArgs on every rank if any shard holds a malformed blob,
+    commitment or proof (the reference's first-error abort, src/kzg.rs:671-683, seen from outside)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    lo, hi = shard_range(n_total, rank, world)
+    n_local = hi - lo
+    blobs, commitments, proofs = _u8(blobs), _u8(commitments), _u8(proofs)
+    if commitments.size != 48 * n_local or proofs.size != 48 * n_local:
+        raise _k.BadArgs("shard does not match shard_range(n_total, rank, world)")
+    if n_total == 0:
+        return True
+    rc, zy = backend.phase_a(blobs, commitments, proofs) if n_local else (0, np.zeros(0, np.uint8))
+    if world > 1:
+        flag = torch.tensor([rc], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        rc = int(flag.item())
+    if rc:
+        _k._raise(rc, "verify_blob_kzg_proof_batch (phase A)")
+    if world > 1:
+        counts = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
+        all_c = _all_gather_bytes(commitments, [48 * c for c in counts], device)
+        all_p = _all_gather_bytes(proofs, [48 * c for c in counts], device)
+        all_zy = _all_gather_bytes(zy, [64 * c for c in counts], device)
+    else:
+        all_c, all_p, all_zy = commitments, proofs, zy
+    r = backend.compute_r(all_c, all_zy, all_p)       # every rank hashes the same bytes: no broadcast needed
+    rc, part = backend.phase_b(commitments, zy, proofs, r, lo)
+    if world > 1:
+        flag = torch.tensor([rc], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        rc = int(flag.item())
+        parts = _all_gather_bytes(part, [224] * world, device)
+    else:
+        parts = part
+    if rc:
+        _k._raise(rc, "verify_blob_kzg_proof_batch (phase B)")
+    return backend.finish(parts)

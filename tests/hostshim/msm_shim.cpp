@@ -14,53 +14,62 @@ static void run_level(const Policy &pol, uint64_t total, int T, int k) {
 }
 static uint32_t bitrev(uint32_t v, int n) { uint32_t r = 0; for (int o = n; o > 1; o >>= 1) { r = (r << 1) | (v & 1); v >>= 1; } return r; }
 
+static int build_table(std::vector<g1_affine_t> &table, const uint8_t *g1_bytes, int n, int c, int T, int k) {
+    const uint32_t D = 1u << (c - 1);
+    table.resize((size_t)n * D);
+    for (int i = 0; i < n; i++) {
+        g1_affine_t p;
+        if (g1_decode_thread(p, g1_bytes + 48 * bitrev(i, n), false)) return KZG_BADARGS;
+        table[(size_t)i * D] = p;
+    }
+    for (int L = 0; L + 1 < c; L++) {
+        TableLevelPolicy pol{table.data(), D, (uint32_t)L};
+        run_level(pol, (uint64_t)n << L, T, k);
+    }
+    return 0;
+}
+
 extern "C" int shim_commit(const uint8_t *g1_bytes, int n, int c, const uint8_t *blobs, int B, uint8_t *out,
                            int *status, int T, int k) {
     const int W = msm_num_windows(c);
     const uint32_t D = 1u << (c - 1);
-    std::vector<g1_affine_t> table((size_t)W * n * D);
-    for (int i = 0; i < n; i++) {
-        g1_affine_t p;
-        if (g1_decode_thread(p, g1_bytes + 48 * bitrev(i, n), false)) return KZG_BADARGS;
-        table[(size_t)i * D] = p;
-    }
-    for (int i = 0; i < n; i++) window_base_thread(table.data(), i, n, c, W, D);
-    for (int L = 0; L + 1 < c; L++) {
-        TableLevelPolicy pol{table.data(), D, (uint32_t)L};
-        run_level(pol, (uint64_t)W * n << L, T, k);
-    }
-    std::vector<int16_t> digits((size_t)B * W * n);
+    std::vector<g1_affine_t> table;
+    if (build_table(table, g1_bytes, n, c, T, k)) return KZG_BADARGS;
+    std::vector<int32_t> digits((size_t)B * W * n);
     for (int b = 0; b < B; b++) status[b] = 0;
     for (uint64_t e = 0; e < (uint64_t)B * n; e++) blob_digits_thread(blobs, e, n, c, W, digits.data(), status);
     uint32_t per_blob = W * n, cnt = per_blob / 2;
     std::vector<g1_affine_t> a((size_t)B * cnt), b2((size_t)B * cnt);
-    GatherPolicy gp{table.data(), digits.data(), a.data(), per_blob, D};
+    GatherPolicy gp{table.data(), digits.data(), a.data(), per_blob, (uint32_t)n - 1, D};
     run_level(gp, (uint64_t)B * cnt, T, k);
     g1_affine_t *in = a.data(), *o = b2.data();
-    while (cnt > 1) {
-        uint32_t nxt = (cnt + 1) / 2;
-        TreePolicy tp{in, o, cnt, nxt};
+    while (cnt > (uint32_t)W) {
+        uint32_t nxt = cnt / 2;
+        PairPolicy tp{in, o};
         run_level(tp, (uint64_t)B * nxt, T, k);
         std::swap(in, o);
         cnt = nxt;
     }
-    for (int b = 0; b < B; b++) g1a_compress(out + 48 * b, in[b]);
+    for (int b = 0; b < B; b++) {
+        g1_affine_t p;
+        horner_thread(p, in + (size_t)b * W, c, W);
+        g1a_compress(out + 48 * b, p);
+    }
     return 0;
 }
 
 // The precomputed table alone (same layout as the device table), for debugging / tests.
-extern "C" int shim_table(const uint8_t *g1_bytes, int n, int c, g1_affine_t *table, int T, int k) {
-    const int W = msm_num_windows(c);
-    const uint32_t D = 1u << (c - 1);
-    for (int i = 0; i < n; i++) {
-        g1_affine_t p;
-        if (g1_decode_thread(p, g1_bytes + 48 * bitrev(i, n), false)) return KZG_BADARGS;
-        table[(size_t)i * D] = p;
-    }
-    for (int i = 0; i < n; i++) window_base_thread(table, i, n, c, W, D);
-    for (int L = 0; L + 1 < c; L++) {
-        TableLevelPolicy pol{table, D, (uint32_t)L};
-        run_level(pol, (uint64_t)W * n << L, T, k);
-    }
+extern "C" int shim_table(const uint8_t *g1_bytes, int n, int c, g1_affine_t *table_out, int T, int k) {
+    std::vector<g1_affine_t> table;
+    if (build_table(table, g1_bytes, n, c, T, k)) return KZG_BADARGS;
+    memcpy(table_out, table.data(), table.size() * sizeof(g1_affine_t));
     return 0;
+}
+// signed-digit recoding of one canonical scalar (8 little-endian words) for a given window
+extern "C" int shim_recode(const uint32_t *scalar, int c, int32_t *digits_out) {
+    fr_t s;
+    memcpy(s.l, scalar, 32);
+    int W = msm_num_windows(c);
+    recode_signed(s, c, W, digits_out, 1);
+    return W;
 }

@@ -1,0 +1,189 @@
+"""CPU tests (no GPU): the host code path of the product's own headers (the same templates
+the CUDA kernels are built from), the host-side pairing, and the C-ABI surface.
+
+  * field arithmetic of kzg_rust_b200/csrc/bigint.cuh vs Python integers
+  * the whole commitment pipeline (table -> digits -> gather level -> tree levels -> Horner ->
+    compress) walked thread by thread on the CPU for the n = 4 preset, vs the oracle
+  * signed-digit recoding invariants for every window width
+  * libkzg_b200.so loads and exports every symbol include/kzg_b200.h declares
+  * the host pairing (stand-in for blst's) vs the oracle's
+"""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from golden_util import golden
+from gpu_util import minimal_setup_bytes, oracle_settings
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM_DIR = os.path.join(ROOT, "tests", "hostshim")
+P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+
+
+def _build_shim(name):
+    src = os.path.join(SHIM_DIR, name + ".cpp")
+    out = os.path.join(SHIM_DIR, "lib" + name + ".so")
+    deps = [src] + [os.path.join(ROOT, "kzg_rust_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "kzg_rust_b200", "csrc"))]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src])
+    return ctypes.CDLL(out)
+
+
+@pytest.fixture(scope="module")
+def field():
+    return _build_shim("field_shim")
+
+
+@pytest.fixture(scope="module")
+def msm():
+    return _build_shim("msm_shim")
+
+
+def _limbs(v, n):
+    return (ctypes.c_uint32 * n)(*[(v >> (32 * i)) & 0xffffffff for i in range(n)])
+
+
+def _val(arr):
+    return sum(int(x) << (32 * i) for i, x in enumerate(arr))
+
+
+def test_fp_and_fr_arithmetic_vs_python(field):
+    rng = np.random.default_rng(1)
+    edge_p = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, 2 ** 380, 2 ** 381 - 1 - (2 ** 381 - 1 - (P - 1))]
+    vals_p = edge_p + [int.from_bytes(rng.bytes(48), "big") % P for _ in range(200)]
+    Rp = pow(2, 384, P)
+    Rp_inv = pow(Rp, -1, P)
+    out = (ctypes.c_uint32 * 12)()
+    for i in range(len(vals_p) - 1):
+        a, b = vals_p[i], vals_p[i + 1]
+        field.shim_fp_mul(_limbs(a, 12), _limbs(b, 12), out)
+        assert _val(out) == a * b * Rp_inv % P
+        field.shim_fp_add(_limbs(a, 12), _limbs(b, 12), out)
+        assert _val(out) == (a + b) % P
+        field.shim_fp_sub(_limbs(a, 12), _limbs(b, 12), out)
+        assert _val(out) == (a - b) % P
+    for a in vals_p[1:20]:
+        am = a * Rp % P
+        field.shim_fp_inv(_limbs(am, 12), out)
+        assert _val(out) == pow(a, -1, P) * Rp % P
+        sq = a * a % P
+        ok = field.shim_fp_sqrt(_limbs(sq * Rp % P, 12), out)
+        assert ok and _val(out) * Rp_inv % P in (a, P - a)
+        assert bool(field.shim_fp_large(_limbs(am, 12))) == (a > (P - 1) // 2)
+    Rr = pow(2, 256, R)
+    Rr_inv = pow(Rr, -1, R)
+    vals_r = [0, 1, R - 1, R - 2, 2 ** 254] + [int.from_bytes(rng.bytes(32), "big") % R for _ in range(200)]
+    out8 = (ctypes.c_uint32 * 8)()
+    for i in range(len(vals_r) - 1):
+        a, b = vals_r[i], vals_r[i + 1]
+        field.shim_fr_mul(_limbs(a, 8), _limbs(b, 8), out8)
+        assert _val(out8) == a * b * Rr_inv % R
+        field.shim_fr_add(_limbs(a, 8), _limbs(b, 8), out8)
+        assert _val(out8) == (a + b) % R
+        field.shim_fr_sub(_limbs(a, 8), _limbs(b, 8), out8)
+        assert _val(out8) == (a - b) % R
+    for a in vals_r[1:12]:
+        field.shim_fr_inv(_limbs(a * Rr % R, 8), out8)
+        assert _val(out8) == pow(a, -1, R) * Rr % R
+    assert field.shim_fr_canonical(_limbs(R - 1, 8)) and not field.shim_fr_canonical(_limbs(R, 8))
+    assert not field.shim_fr_canonical(_limbs(2 ** 256 - 1, 8))
+
+
+@pytest.mark.parametrize("c", list(range(2, 21)))
+def test_signed_digit_recoding(msm, c):
+    rng = np.random.default_rng(c)
+    vals = [0, 1, R - 1, R - 2, 2 ** 254, 2 ** 248 - 1] + [int.from_bytes(rng.bytes(32), "big") % R for _ in range(50)]
+    digs = (ctypes.c_int32 * 130)()
+    for v in vals:
+        W = msm.shim_recode(_limbs(v, 8), c, digs)
+        assert W * c >= 255
+        assert all(abs(digs[j]) <= 1 << (c - 1) for j in range(W))
+        assert sum(digs[j] << (c * j) for j in range(W)) == v
+
+
+@pytest.mark.parametrize("c,T,k", [(2, 4, 3), (5, 8, 4), (6, 32, 1), (9, 16, 64)])
+def test_commit_pipeline_on_cpu_minimal_preset(msm, c, T, k):
+    """The product's own pipeline, thread by thread on the CPU, for kzg_minimal."""
+    g1, _ = minimal_setup_bytes()
+    o = oracle_settings("minimal")
+    rng = np.random.default_rng(100 + c)
+    rows = [[0, 0, 0, 0], [R - 1] * 4, [1, 0, 0, 0], [0, 0, 5, 0], [7, 7, 7, 7], [R, 0, 0, 0]]
+    rows += [[int.from_bytes(rng.bytes(32), "big") % R for _ in range(4)] for _ in range(10)]
+    blobs = b"".join(b"".join(v.to_bytes(32, "big") for v in row) for row in rows)
+    B = len(rows)
+    out = ctypes.create_string_buffer(48 * B)
+    status = (ctypes.c_int * B)()
+    assert msm.shim_commit(g1, 4, c, blobs, B, out, status, T, k) == 0
+    from oracle.binding import OracleError
+    for i in range(B):
+        try:
+            exp = o.blob_to_kzg_commitment(blobs[128 * i:128 * i + 128])
+        except OracleError:
+            assert status[i] == 1
+            continue
+        assert status[i] == 0 and out.raw[48 * i:48 * i + 48] == exp, i
+
+
+def test_library_exports_every_declared_symbol():
+    """No compute calls (no GPU here): the C-ABI library loads and exports what the header declares."""
+    import kzg_rust_b200 as k
+    L = k.load_library()
+    with open(os.path.join(ROOT, "include", "kzg_b200.h")) as fh:
+        text = fh.read()
+    names = sorted(set(re.findall(r"\b(kzg_b200_[a-z0-9_]+)\s*\(", text)))
+    assert len(names) >= 20
+    for nm in names:
+        assert hasattr(L, nm), nm
+
+
+def test_missing_device_is_reported_not_papered_over():
+    """Without a usable CUDA device context creation fails with the CUDA error code; there is no CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import kzg_rust_b200 as k
+    g = golden()
+    with pytest.raises(k.Error):
+        k.KzgSettings.load_trusted_setup(g.g1_bytes, g.g2_bytes, 0, 4)
+
+
+def test_host_pairing_vs_oracle():
+    from oracle import binding as ob
+    import kzg_rust_b200 as k
+    L = k.load_library()
+    G = golden()
+    g1 = [G.g1_bytes[48 * i:48 * i + 48] for i in range(4)]
+    g2 = [G.g2_bytes[96 * i:96 * i + 96] for i in range(3)]
+    tau = (1337).to_bytes(32, "big")
+    tau_p = ob.g1_lincomb([g1[2]], [tau])
+    inf = bytes([0xC0]) + bytes(47)
+    cases = [(g1[2], g2[1], tau_p, g2[0]), (g1[1], g2[0], g1[0], g2[1]), (g1[3], g2[1], tau_p, g2[0]),
+             (g1[2], g2[2], ob.g1_lincomb([tau_p], [tau]), g2[0]), (inf, g2[1], inf, g2[0]), (inf, g2[1], g1[0], g2[0])]
+    for a1, a2, b1, b2 in cases:
+        ok = ctypes.c_int(-1)
+        assert L.kzg_b200_pairings_verify(a1, a2, b1, b2, ctypes.byref(ok)) == 0
+        assert bool(ok.value) is ob.pairings_verify(a1, a2, b1, b2)
+    ok = ctypes.c_int(-1)
+    assert L.kzg_b200_pairings_verify(bytes(48), g2[1], g1[0], g2[0], ctypes.byref(ok)) != 0  # bit 7 clear: bad encoding
+
+
+def test_host_types_mirror_reference_length_checks():
+    """reference src/kzg.rs:107-117, 130-141, 160-173."""
+    import kzg_rust_b200 as k
+    with pytest.raises(k.Error):
+        k.Blob.from_bytes(bytes(131071))
+    with pytest.raises(k.Error):
+        k.Bytes48.from_bytes(bytes(47))
+    with pytest.raises(k.BadArgs):
+        k.Bytes32.from_bytes(bytes(33))
+    with pytest.raises(k.InvalidHexFormat):
+        k.hex_to_bytes("0xzz")
+    assert k.Bytes48.from_hex("0x" + "ab" * 48).to_bytes() == bytes([0xab]) * 48
+    with pytest.raises(k.BadArgs):
+        k.Kzg.verify_blob_kzg_proof_batch([k.Blob(bytes(131072))], [], [], None)
+    assert k.Kzg.verify_blob_kzg_proof_batch([], [], [], None) is True
