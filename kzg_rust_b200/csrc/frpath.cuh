@@ -313,10 +313,10 @@ __global__ void __launch_bounds__(KZG_EVAL_THREADS) k_eval_quotient(
 // (reference verify_kzg_proof_batch src/kzg.rs:579-627 and compute_r_powers
 // src/utils.rs:426-474; sum_i r_i [y_i]G is folded into one scalar).
 // Shamir's trick shares the doublings of the two multiplications that make up U_i.
-// out_pts[i] = V_i, out_pts[count + i] = U_i (affine), sy[i] = s_i (Montgomery).
+// out_pts[i] = V_i, out_pts[count + i] = U_i (Jacobian), sy[i] = s_i (Montgomery).
 __global__ void __launch_bounds__(64) k_verify_terms(const g1_affine_t *__restrict__ cpts, const g1_affine_t *__restrict__ ppts,
                                                      const uint8_t *__restrict__ zy, fr_t r_canon, uint64_t first,
-                                                     uint32_t count, g1_affine_t *__restrict__ out_pts, fr_t *__restrict__ sy) {
+                                                     uint32_t count, g1_jac_t *__restrict__ out_pts, fr_t *__restrict__ sy) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     fr_t r, ri = fe_one<FrParams>();
@@ -356,11 +356,40 @@ __global__ void __launch_bounds__(64) k_verify_terms(const g1_affine_t *__restri
         if (ba && !c_inf) g1j_add_affine(U, U, C.x, C.y);
         if (bb && !p_inf) g1j_add_affine(U, U, P.x, P.y);
     }
-    g1_affine_t a;
-    g1j_to_affine(a, V);
-    out_pts[i] = a;
-    g1j_to_affine(a, U);
-    out_pts[count + i] = a;
+    out_pts[i] = V;
+    out_pts[count + i] = U;
+}
+// block b adds the `count` Jacobian points pts[b*count ..] -> out[b] (affine): strided partial
+// sums per thread, then a shared-memory tree.  The sums of batch verification are a few
+// thousand points at most, so one block each beats a log-depth chain of launches.
+#define KZG_JSUM_THREADS 128
+__global__ void __launch_bounds__(KZG_JSUM_THREADS) k_jac_sum(const g1_jac_t *__restrict__ pts, uint32_t count,
+                                                              g1_affine_t *__restrict__ out) {
+    __shared__ g1_jac_t red[KZG_JSUM_THREADS];
+    const g1_jac_t *base = pts + (size_t)blockIdx.x * count;
+    g1_jac_t acc;
+    g1j_set_inf(acc);
+#pragma unroll 1
+    for (uint32_t i = threadIdx.x; i < count; i += KZG_JSUM_THREADS) {
+        g1_jac_t t = base[i];
+        g1j_add(acc, acc, t);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+#pragma unroll 1
+    for (int s = KZG_JSUM_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            g1_jac_t a = red[threadIdx.x], b = red[threadIdx.x + s];
+            g1j_add(a, a, b);
+            red[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        g1_affine_t a;
+        g1j_to_affine(a, red[0]);
+        out[blockIdx.x] = a;
+    }
 }
 // sum of `count` Montgomery scalars -> out[0] (one CTA)
 __global__ void __launch_bounds__(256) k_fr_sum(const fr_t *__restrict__ in, uint32_t count, fr_t *__restrict__ out) {

@@ -122,6 +122,36 @@ KZG_HD void g1j_add_affine(g1_jac_t &r, const g1_jac_t &p, const fp_t &qx, const
     fe_add(t, p.z, h); fe_sqr(t, t); fe_sub(t, t, z1z1); fe_sub(z3, t, hh);
     r.x = x3; r.y = y3; r.z = z3;
 }
+// r = p + q, both Jacobian, complete
+KZG_HD void g1j_add(g1_jac_t &r, const g1_jac_t &p, const g1_jac_t &q) {
+    if (g1j_is_inf(p)) { r = q; return; }
+    if (g1j_is_inf(q)) { r = p; return; }
+    fp_t z1z1, z2z2, u1, u2, s1, s2, h, i, j, rr, v, t;
+    fe_sqr(z1z1, p.z);
+    fe_sqr(z2z2, q.z);
+    fe_mul(u1, p.x, z2z2);
+    fe_mul(u2, q.x, z1z1);
+    fe_mul(s1, p.y, q.z); fe_mul(s1, s1, z2z2);
+    fe_mul(s2, q.y, p.z); fe_mul(s2, s2, z1z1);
+    if (fe_eq(u1, u2)) {
+        if (fe_eq(s1, s2)) { g1j_dbl(r, p); return; }
+        g1j_set_inf(r);
+        return;
+    }
+    fe_sub(h, u2, u1);
+    fe_dbl(i, h); fe_sqr(i, i);
+    fe_mul(j, h, i);
+    fe_sub(rr, s2, s1); fe_dbl(rr, rr);
+    fe_mul(v, u1, i);
+    fp_t x3, y3, z3;
+    fe_sqr(x3, rr); fe_sub(x3, x3, j); fe_dbl(t, v); fe_sub(x3, x3, t);
+    fe_sub(t, v, x3); fe_mul(t, rr, t);
+    fe_mul(s1, s1, j); fe_dbl(s1, s1);
+    fe_sub(y3, t, s1);
+    fe_add(t, p.z, q.z); fe_sqr(t, t); fe_sub(t, t, z1z1); fe_sub(t, t, z2z2);
+    fe_mul(z3, t, h);
+    r.x = x3; r.y = y3; r.z = z3;
+}
 KZG_HD void g1j_to_affine(g1_affine_t &r, const g1_jac_t &p) {
     if (g1j_is_inf(p)) { g1a_set_inf(r); return; }
     fp_t zi, zi2, zi3;
@@ -209,8 +239,33 @@ KZG_HD bool g1a_uncompress(g1_affine_t &out, const uint8_t in[48]) {
     out.y = y;
     return true;
 }
-// blst_p1_in_g1 stand-in: P has order dividing r  <=>  [r]P == infinity
+// blst_p1_in_g1 stand-in.  For BLS12 curves P lies in G1 exactly when phi(P) = -[x^2]P, with
+// phi(x, y) = (beta x, y) the endomorphism acting on G1 as multiplication by -x^2 and x the
+// curve parameter (M. Scott, "A note on group membership tests for G1, G2 and GT on BLS
+// pairing-friendly curves", 2021): one 128-bit multiplication instead of the 255-bit [r]P.
+// P must be on the curve and not infinity.
 KZG_HD bool g1a_in_subgroup(const g1_affine_t &p) {
+    uint32_t k[4] = {BLS_X_SQUARED_LIMBS};
+    g1_jac_t q;
+    g1j_mul(q, p, k, 128);
+    if (g1j_is_inf(q)) return false;
+    fp_t beta, z2, z3, t;
+    {
+        constexpr uint32_t bm[12] = {FP_BETA_MONT_LIMBS};
+#pragma unroll
+        for (int i = 0; i < 12; i++) beta.l[i] = bm[i];
+    }
+    fe_sqr(z2, q.z);
+    fe_mul(z3, z2, q.z);
+    fe_mul(t, p.x, beta);
+    fe_mul(t, t, z2);
+    if (!fe_eq(t, q.x)) return false;
+    fe_mul(t, p.y, z3);
+    fe_neg(t, t);
+    return fe_eq(t, q.y);
+}
+// the defining test, [r]P == infinity (kept for cross-checks)
+KZG_HD bool g1a_in_subgroup_by_order(const g1_affine_t &p) {
     uint32_t k[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) k[i] = FrParams::mod(i);

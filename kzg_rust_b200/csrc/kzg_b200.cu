@@ -37,6 +37,7 @@ using namespace kzg;
     } while (0)
 
 // ------------------------------------------------------------------ context
+#define KZG_SLOTS 3
 struct kzg_b200_ctx {
     int device = 0;
     int n = 0;        // FIELD_ELEMENTS_PER_BLOB
@@ -49,21 +50,36 @@ struct kzg_b200_ctx {
     g1_affine_t *d_table = nullptr;
     fr_t *d_roots = nullptr;       // roots of unity, Montgomery form, bit-reversed (src/kzg.rs:764-799)
     uint8_t g2_tau[96];            // [tau]G2 = g2_values[1]
-    // workspace for one chunk of blobs
+    // Work is cut into chunks of `chunk` blobs.  Two chunks are in flight at a time, each on its
+    // own lane (stream + workspace), so the latency-bound end of one chunk (the small levels of the
+    // addition tree, the Horner pass) runs under the big levels of the next.  Lane 0 launches on
+    // `stream`, the stream callers synchronise with; `cur` is the lane of the chunk being enqueued
+    // (calls on a context are serialised by `mu`).
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        int32_t *d_digits = nullptr;
+        g1_affine_t *d_buf_a = nullptr, *d_buf_b = nullptr;
+        fp_t *d_scratch = nullptr;
+        size_t scratch_elems = 0;
+        fr_t *d_poly = nullptr;           // chunk x n Montgomery evaluations (proof / verify paths)
+        fr_t *d_inv = nullptr;            // chunk x n prefix products, then 1/(z - w_i)
+        fr_t *d_z = nullptr;              // chunk challenges / evaluation points (canonical)
+        uint8_t *d_zy = nullptr;          // chunk x 64 B: z || y big-endian
+        g1_affine_t *d_pts = nullptr;     // chunk x 2 decoded commitments / proofs
+        cudaEvent_t ev_done = nullptr;
+    };
+    Lane lanes[2];
+    int nlanes = 2;                   // KZG_B200_LANES
+    Lane *cur = nullptr;
+    cudaEvent_t ev_start = nullptr;
     size_t chunk = 0;
-    int32_t *d_digits = nullptr;
-    g1_affine_t *d_buf_a = nullptr, *d_buf_b = nullptr;
-    fp_t *d_scratch = nullptr;
-    size_t scratch_elems = 0;
-    uint8_t *d_stage_in = nullptr;    // chunk blobs
-    uint8_t *d_stage_aux = nullptr;   // chunk x 96 B (commitments / proofs / z)
-    uint8_t *d_stage_out = nullptr;   // chunk x 96 B
-    int32_t *d_status = nullptr;
-    fr_t *d_poly = nullptr;           // chunk x n Montgomery evaluations (proof / verify paths)
-    fr_t *d_inv = nullptr;            // chunk x n prefix products, then 1/(z - w_i)
-    fr_t *d_z = nullptr;              // chunk challenges / evaluation points (canonical)
-    uint8_t *d_zy = nullptr;          // chunk x 64 B: z || y big-endian
-    g1_affine_t *d_pts = nullptr;     // chunk x 2 decoded commitments / proofs
+    // host-call staging, KZG_SLOTS slots: chunks i+1, i+2 are uploaded on copy_stream while chunk i computes
+    uint8_t *d_stage_in = nullptr;    // slots x chunk blobs
+    uint8_t *d_stage_aux = nullptr;   // slots x chunk x 96 B (commitments / proofs / z)
+    uint8_t *d_stage_out = nullptr;   // slots x chunk x 96 B
+    int32_t *d_status = nullptr;      // slots x chunk
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d[KZG_SLOTS] = {nullptr, nullptr, nullptr}, ev_free[KZG_SLOTS] = {nullptr, nullptr, nullptr};
     host_g2_prepared *tau_prepared = nullptr;  // Miller-loop lines of [tau]G2
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
@@ -76,6 +92,11 @@ struct kzg_b200_ctx {
     std::mutex mu;
 };
 
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
 // ------------------------------------------------------------------ stage timing
 static void stage_begin(kzg_b200_ctx *ctx, int stage) {
     if (!ctx->profile) return;
@@ -83,12 +104,12 @@ static void stage_begin(kzg_b200_ctx *ctx, int stage) {
     r.stage = stage;
     cudaEventCreate(&r.a);
     cudaEventCreate(&r.b);
-    cudaEventRecord(r.a, ctx->stream);
+    cudaEventRecord(r.a, ctx->cur->stream);
     ctx->pending.push_back(r);
 }
 static void stage_end(kzg_b200_ctx *ctx, uint64_t launches) {
     if (!ctx->profile || ctx->pending.empty()) return;
-    cudaEventRecord(ctx->pending.back().b, ctx->stream);
+    cudaEventRecord(ctx->pending.back().b, ctx->cur->stream);
     ctx->stage_launches[ctx->pending.back().stage] += launches;
 }
 static void stage_collect(kzg_b200_ctx *ctx) {  // stream must be idle
@@ -220,12 +241,13 @@ __global__ void __launch_bounds__(128, 4) k_peak_fpmul(fp_t *out, int iters) {
 static inline unsigned blocks_for(uint64_t total, unsigned tpb) { return (unsigned)((total + tpb - 1) / tpb); }
 
 static int ensure_scratch(kzg_b200_ctx *ctx, size_t elems) {
-    if (elems <= ctx->scratch_elems) return KZG_B200_OK;
-    if (ctx->d_scratch) CU(cudaFree(ctx->d_scratch));
-    ctx->d_scratch = nullptr;
-    ctx->scratch_elems = 0;
-    CU(cudaMalloc(&ctx->d_scratch, elems * sizeof(fp_t)));
-    ctx->scratch_elems = elems;
+    kzg_b200_ctx::Lane *ln = ctx->cur;
+    if (elems <= ln->scratch_elems) return KZG_B200_OK;
+    if (ln->d_scratch) CU(cudaFree(ln->d_scratch));
+    ln->d_scratch = nullptr;
+    ln->scratch_elems = 0;
+    CU(cudaMalloc(&ln->d_scratch, elems * sizeof(fp_t)));
+    ln->scratch_elems = elems;
     return KZG_B200_OK;
 }
 
@@ -246,9 +268,9 @@ static int launch_batch_add(kzg_b200_ctx *ctx, const Policy &pol, uint64_t total
     }
     RC(ensure_scratch(ctx, (size_t)(T * k)));
     if (ctx->add_blocks >= 4)
-        batch_add_kernel<Policy, 4><<<(unsigned)(T / tpb), tpb, 0, ctx->stream>>>(pol, total, ctx->d_scratch, k);
+        batch_add_kernel<Policy, 4><<<(unsigned)(T / tpb), tpb, 0, ctx->cur->stream>>>(pol, total, ctx->cur->d_scratch, k);
     else
-        batch_add_kernel<Policy, 3><<<(unsigned)(T / tpb), tpb, 0, ctx->stream>>>(pol, total, ctx->d_scratch, k);
+        batch_add_kernel<Policy, 3><<<(unsigned)(T / tpb), tpb, 0, ctx->cur->stream>>>(pol, total, ctx->cur->d_scratch, k);
     ctx->launches++;
     CU(cudaGetLastError());
     return KZG_B200_OK;
@@ -258,11 +280,12 @@ static int launch_batch_add(kzg_b200_ctx *ctx, const Policy &pol, uint64_t total
 // (*out)[b*W + j] = S_j of blob b
 static int run_msm(kzg_b200_ctx *ctx, size_t count, const g1_affine_t **out) {
     uint32_t per_blob = (uint32_t)ctx->W * ctx->n, cnt = per_blob / 2;
-    GatherPolicy gp{ctx->d_table, ctx->d_digits, ctx->d_buf_a, per_blob, (uint32_t)ctx->n - 1, ctx->D};
+    kzg_b200_ctx::Lane *ln = ctx->cur;
+    GatherPolicy gp{ctx->d_table, ln->d_digits, ln->d_buf_a, per_blob, (uint32_t)ctx->n - 1, ctx->D};
     stage_begin(ctx, KZG_B200_STAGE_MSM_GATHER);
     RC(launch_batch_add(ctx, gp, (uint64_t)count * cnt));
     stage_end(ctx, 1);
-    g1_affine_t *in = ctx->d_buf_a, *o = ctx->d_buf_b;
+    g1_affine_t *in = ln->d_buf_a, *o = ln->d_buf_b;
     stage_begin(ctx, KZG_B200_STAGE_MSM_TREE);
     uint64_t levels = 0;
     while (cnt > (uint32_t)ctx->W) {  // n is a power of two: pairs never straddle two windows
@@ -281,45 +304,70 @@ static int run_msm(kzg_b200_ctx *ctx, size_t count, const g1_affine_t **out) {
 // ------------------------------------------------------------------ workspace
 static size_t per_blob_workspace(const kzg_b200_ctx *ctx) {
     size_t wn = (size_t)ctx->W * ctx->n;
-    return wn * 4 /*digits*/ + wn / 2 * sizeof(g1_affine_t) + (wn / 4 + 1) * sizeof(g1_affine_t) +
-           (size_t)ctx->n * 32 /*stage in*/ + 2 * (size_t)ctx->n * sizeof(fr_t) /*poly, inv*/ + 96 * 2 + 64 + sizeof(fr_t) +
-           2 * sizeof(g1_affine_t) + 4;
+    size_t lane = wn * 4 /*digits*/ + wn / 2 * sizeof(g1_affine_t) + (wn / 4 + 1) * sizeof(g1_affine_t) +
+                  2 * (size_t)ctx->n * sizeof(fr_t) /*poly, inv*/ + 64 + sizeof(fr_t) + 2 * sizeof(g1_affine_t) +
+                  (wn / 2) * sizeof(fp_t) /*scratch of the gather level*/;
+    return ctx->nlanes * lane + KZG_SLOTS * ((size_t)ctx->n * 32 + 96 * 2 + 4);
 }
 static void free_workspace(kzg_b200_ctx *ctx) {
-    cudaFree(ctx->d_digits); cudaFree(ctx->d_buf_a); cudaFree(ctx->d_buf_b); cudaFree(ctx->d_stage_in);
-    cudaFree(ctx->d_stage_aux); cudaFree(ctx->d_stage_out); cudaFree(ctx->d_status); cudaFree(ctx->d_poly);
-    cudaFree(ctx->d_inv); cudaFree(ctx->d_z); cudaFree(ctx->d_zy); cudaFree(ctx->d_pts);
-    ctx->d_digits = nullptr; ctx->d_buf_a = ctx->d_buf_b = nullptr; ctx->d_stage_in = ctx->d_stage_aux = ctx->d_stage_out = nullptr;
-    ctx->d_status = nullptr; ctx->d_poly = nullptr; ctx->d_inv = nullptr; ctx->d_z = nullptr; ctx->d_zy = nullptr; ctx->d_pts = nullptr;
+    for (auto &ln : ctx->lanes) {
+        cudaFree(ln.d_digits); cudaFree(ln.d_buf_a); cudaFree(ln.d_buf_b); cudaFree(ln.d_poly); cudaFree(ln.d_inv);
+        cudaFree(ln.d_z); cudaFree(ln.d_zy); cudaFree(ln.d_pts); cudaFree(ln.d_scratch);
+        ln.d_digits = nullptr; ln.d_buf_a = ln.d_buf_b = nullptr; ln.d_poly = ln.d_inv = ln.d_z = nullptr;
+        ln.d_zy = nullptr; ln.d_pts = nullptr; ln.d_scratch = nullptr; ln.scratch_elems = 0;
+    }
+    cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_aux); cudaFree(ctx->d_stage_out); cudaFree(ctx->d_status);
+    ctx->d_stage_in = ctx->d_stage_aux = ctx->d_stage_out = nullptr;
+    ctx->d_status = nullptr;
     ctx->chunk = 0;
 }
 static int alloc_workspace(kzg_b200_ctx *ctx, size_t chunk) {
     free_workspace(ctx);
     size_t wn = (size_t)ctx->W * ctx->n;
-    CU(cudaMalloc(&ctx->d_digits, chunk * wn * sizeof(int32_t)));
-    CU(cudaMalloc(&ctx->d_buf_a, chunk * (wn / 2) * sizeof(g1_affine_t)));
-    CU(cudaMalloc(&ctx->d_buf_b, chunk * (wn / 4 + 1) * sizeof(g1_affine_t)));
-    CU(cudaMalloc(&ctx->d_stage_in, chunk * (size_t)ctx->n * 32));
-    CU(cudaMalloc(&ctx->d_stage_aux, chunk * 96));
-    CU(cudaMalloc(&ctx->d_stage_out, chunk * 96));
-    CU(cudaMalloc(&ctx->d_status, chunk * sizeof(int32_t)));
-    CU(cudaMalloc(&ctx->d_poly, chunk * (size_t)ctx->n * sizeof(fr_t)));
-    CU(cudaMalloc(&ctx->d_inv, chunk * (size_t)ctx->n * sizeof(fr_t)));
-    CU(cudaMalloc(&ctx->d_z, chunk * sizeof(fr_t)));
-    CU(cudaMalloc(&ctx->d_zy, chunk * 64));
-    CU(cudaMalloc(&ctx->d_pts, chunk * 2 * sizeof(g1_affine_t)));
+    for (int l = 0; l < ctx->nlanes; l++) {
+        kzg_b200_ctx::Lane &ln = ctx->lanes[l];
+        CU(cudaMalloc(&ln.d_digits, chunk * wn * sizeof(int32_t)));
+        CU(cudaMalloc(&ln.d_buf_a, chunk * (wn / 2) * sizeof(g1_affine_t)));
+        CU(cudaMalloc(&ln.d_buf_b, chunk * (wn / 4 + 1) * sizeof(g1_affine_t)));
+        CU(cudaMalloc(&ln.d_poly, chunk * (size_t)ctx->n * sizeof(fr_t)));
+        CU(cudaMalloc(&ln.d_inv, chunk * (size_t)ctx->n * sizeof(fr_t)));
+        CU(cudaMalloc(&ln.d_z, chunk * sizeof(fr_t)));
+        CU(cudaMalloc(&ln.d_zy, chunk * 64));
+        CU(cudaMalloc(&ln.d_pts, chunk * 2 * sizeof(g1_affine_t)));
+    }
+    CU(cudaMalloc(&ctx->d_stage_in, KZG_SLOTS * chunk * (size_t)ctx->n * 32));
+    CU(cudaMalloc(&ctx->d_stage_aux, KZG_SLOTS * chunk * 96));
+    CU(cudaMalloc(&ctx->d_stage_out, KZG_SLOTS * chunk * 96));
+    CU(cudaMalloc(&ctx->d_status, KZG_SLOTS * chunk * sizeof(int32_t)));
     ctx->chunk = chunk;
     return KZG_B200_OK;
 }
 
-// ------------------------------------------------------------------ context creation
-static int env_int(const char *name, int dflt) {
-    const char *v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
+// Chunks of one call alternate between the lanes.  lanes_begin makes the extra lane wait for what is
+// already queued on the caller-visible stream, lanes_end makes that stream wait for the extra lane.
+static int lanes_in_use(const kzg_b200_ctx *ctx) { return ctx->profile ? 1 : ctx->nlanes; }  // profiling wants unoverlapped stages
+static int lanes_begin(kzg_b200_ctx *ctx) {
+    ctx->cur = &ctx->lanes[0];
+    if (lanes_in_use(ctx) > 1) {
+        CU(cudaEventRecord(ctx->ev_start, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->lanes[1].stream, ctx->ev_start, 0));
+    }
+    return KZG_B200_OK;
+}
+static void lane_select(kzg_b200_ctx *ctx, size_t chunk_index) { ctx->cur = &ctx->lanes[chunk_index % lanes_in_use(ctx)]; }
+static int lanes_end(kzg_b200_ctx *ctx) {
+    if (lanes_in_use(ctx) > 1) {
+        CU(cudaEventRecord(ctx->lanes[1].ev_done, ctx->lanes[1].stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->lanes[1].ev_done, 0));
+    }
+    ctx->cur = &ctx->lanes[0];
+    return KZG_B200_OK;
 }
 
+// ------------------------------------------------------------------ context creation
 static int build_table(kzg_b200_ctx *ctx, const uint8_t *g1_bytes) {
     const int n = ctx->n;
+    ctx->cur = &ctx->lanes[0];
     uint8_t *d_bytes = nullptr;
     g1_affine_t *d_dec = nullptr;
     int32_t *d_st = nullptr;
@@ -375,6 +423,17 @@ extern "C" int kzg_b200_ctx_create(const uint8_t *g1_lagrange, size_t n1, const 
     ctx->max_k = env_int("KZG_B200_BATCH_K", 4096);
     ctx->add_blocks = env_int("KZG_B200_ADD_BLOCKS", 3) >= 4 ? 4 : 3;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KZG_B200_CUDA_ERROR; }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { kzg_b200_ctx_destroy(ctx); return KZG_B200_CUDA_ERROR; }
+    ctx->nlanes = env_int("KZG_B200_LANES", 2) >= 2 ? 2 : 1;
+    ctx->lanes[0].stream = ctx->stream;
+    if (cudaStreamCreateWithFlags(&ctx->lanes[1].stream, cudaStreamNonBlocking) != cudaSuccess) { kzg_b200_ctx_destroy(ctx); return KZG_B200_CUDA_ERROR; }
+    ctx->cur = &ctx->lanes[0];
+    bool ev_ok = cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2; i++) ev_ok = ev_ok && cudaEventCreateWithFlags(&ctx->lanes[i].ev_done, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < KZG_SLOTS; i++)
+        ev_ok = ev_ok && cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ev_ok) { kzg_b200_ctx_destroy(ctx); return KZG_B200_CUDA_ERROR; }
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     int c = window_bits > 0 ? window_bits : env_int("KZG_B200_WINDOW_BITS", 0);
@@ -448,11 +507,20 @@ extern "C" void kzg_b200_ctx_destroy(kzg_b200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->lanes[1].stream) cudaStreamSynchronize(ctx->lanes[1].stream);
     free_workspace(ctx);
-    cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_table);
     cudaFree(ctx->d_roots);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->lanes[1].stream) cudaStreamDestroy(ctx->lanes[1].stream);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    for (int i = 0; i < 2; i++)
+        if (ctx->lanes[i].ev_done) cudaEventDestroy(ctx->lanes[i].ev_done);
+    for (int i = 0; i < KZG_SLOTS; i++) {
+        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+        if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
+    }
     stage_collect(ctx);
     host_g2_prepared_free(ctx->tau_prepared);
     delete ctx;
@@ -496,15 +564,16 @@ extern "C" int kzg_b200_profile_read(kzg_b200_ctx *ctx, double *ms_out, uint64_t
 // one chunk, everything on the device: blobs -> digits -> MSM -> 48-byte commitments
 static int commit_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, size_t count, uint8_t *d_out, int32_t *d_status) {
     const uint64_t elems = (uint64_t)count * ctx->n;
-    CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), ctx->stream));
+    cudaStream_t st = ctx->cur->stream;
+    CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), st));
     stage_begin(ctx, KZG_B200_STAGE_DIGITS);
-    k_blob_digits<<<blocks_for(elems, 256), 256, 0, ctx->stream>>>(d_blobs, elems, ctx->n, ctx->c, ctx->W, ctx->d_digits, d_status);
+    k_blob_digits<<<blocks_for(elems, 256), 256, 0, st>>>(d_blobs, elems, ctx->n, ctx->c, ctx->W, ctx->cur->d_digits, d_status);
     stage_end(ctx, 1);
     ctx->launches++;
     const g1_affine_t *res = nullptr;
     RC(run_msm(ctx, count, &res));
     stage_begin(ctx, KZG_B200_STAGE_COMPRESS);
-    k_horner_compress<<<blocks_for(count, 64), 64, 0, ctx->stream>>>(res, ctx->c, ctx->W, d_status, d_out, (uint32_t)count);
+    k_horner_compress<<<blocks_for(count, 64), 64, 0, st>>>(res, ctx->c, ctx->W, d_status, d_out, (uint32_t)count);
     stage_end(ctx, 1);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -517,10 +586,48 @@ extern "C" int kzg_b200_blob_to_kzg_commitment_device(kzg_b200_ctx *ctx, const u
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     const size_t bpb = (size_t)ctx->n * 32;
-    for (size_t off = 0; off < n; off += ctx->chunk) {
+    RC(lanes_begin(ctx));
+    size_t i = 0;
+    for (size_t off = 0; off < n; off += ctx->chunk, i++) {
         size_t cnt = std::min(ctx->chunk, n - off);
+        lane_select(ctx, i);
         RC(commit_chunk(ctx, d_blobs + off * bpb, cnt, d_out + off * 48, d_status + off));
     }
+    return lanes_end(ctx);
+}
+
+// Host-buffer calls run the chunks through KZG_SLOTS staging slots: the uploads of the next chunks
+// (on copy_stream) overlap the kernels of the current ones (one chunk per lane in flight).
+// upload(slot, off, cnt) enqueues the H2D copies of one chunk on copy_stream; run(slot, off, cnt)
+// enqueues kernels + D2H on the current lane's stream.
+template <class Upload, class Run>
+static int staged_chunks(kzg_b200_ctx *ctx, size_t n, Upload upload, Run run) {
+    const size_t nchunks = (n + ctx->chunk - 1) / ctx->chunk;
+    const size_t ahead = KZG_SLOTS - 1;
+    auto enqueue_upload = [&](size_t i) -> int {
+        int slot = (int)(i % KZG_SLOTS);
+        size_t off = i * ctx->chunk, cnt = std::min(ctx->chunk, n - off);
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[slot], 0));  // the chunk that used this slot is done
+        RC(upload(slot, off, cnt));
+        CU(cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_stream));
+        return KZG_B200_OK;
+    };
+    RC(lanes_begin(ctx));
+    // the slots may still be in use by an earlier asynchronous call on `stream`
+    for (int sl = 0; sl < KZG_SLOTS; sl++) CU(cudaEventRecord(ctx->ev_free[sl], ctx->stream));
+    for (size_t i = 0; i < std::min(ahead, nchunks); i++) RC(enqueue_upload(i));
+    for (size_t i = 0; i < nchunks; i++) {
+        int slot = (int)(i % KZG_SLOTS);
+        size_t off = i * ctx->chunk, cnt = std::min(ctx->chunk, n - off);
+        if (i + ahead < nchunks) RC(enqueue_upload(i + ahead));
+        lane_select(ctx, i);
+        CU(cudaStreamWaitEvent(ctx->cur->stream, ctx->ev_h2d[slot], 0));
+        RC(run(slot, off, cnt));
+        CU(cudaEventRecord(ctx->ev_free[slot], ctx->cur->stream));
+    }
+    RC(lanes_end(ctx));
+    CU(cudaStreamSynchronize(ctx->stream));
+    stage_collect(ctx);
     return KZG_B200_OK;
 }
 
@@ -529,16 +636,21 @@ extern "C" int kzg_b200_blob_to_kzg_commitment_batch(kzg_b200_ctx *ctx, const ui
     if (!ctx || (n && (!blobs || !out || !status))) return KZG_B200_BAD_ARGS;
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(cudaSetDevice(ctx->device));
-    const size_t bpb = (size_t)ctx->n * 32;
-    for (size_t off = 0; off < n; off += ctx->chunk) {
-        size_t cnt = std::min(ctx->chunk, n - off);
-        CU(cudaMemcpyAsync(ctx->d_stage_in, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->stream));
-        RC(commit_chunk(ctx, ctx->d_stage_in, cnt, ctx->d_stage_out, ctx->d_status));
-        CU(cudaMemcpyAsync(out + off * 48, ctx->d_stage_out, cnt * 48, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(status + off, ctx->d_status, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-    }
-    return KZG_B200_OK;
+    const size_t bpb = (size_t)ctx->n * 32, ch = ctx->chunk;
+    return staged_chunks(
+        ctx, n,
+        [&](int slot, size_t off, size_t cnt) -> int {
+            CU(cudaMemcpyAsync(ctx->d_stage_in + slot * ch * bpb, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->copy_stream));
+            return KZG_B200_OK;
+        },
+        [&](int slot, size_t off, size_t cnt) -> int {
+            uint8_t *d_out = ctx->d_stage_out + slot * ch * 96;
+            int32_t *d_st = ctx->d_status + slot * ch;
+            RC(commit_chunk(ctx, ctx->d_stage_in + slot * ch * bpb, cnt, d_out, d_st));
+            CU(cudaMemcpyAsync(out + off * 48, d_out, cnt * 48, cudaMemcpyDeviceToHost, ctx->cur->stream));
+            CU(cudaMemcpyAsync(status + off, d_st, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->cur->stream));
+            return KZG_B200_OK;
+        });
 }
 
 // ------------------------------------------------------------------ roofline micro-benchmarks

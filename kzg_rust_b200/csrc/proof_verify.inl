@@ -5,7 +5,7 @@
 static int decode_points(kzg_b200_ctx *ctx, const uint8_t *d_bytes, g1_affine_t *d_out, int32_t *d_status, size_t count,
                          int check_subgroup, size_t status_mod) {
     stage_begin(ctx, KZG_B200_STAGE_VALIDATE);
-    k_decode_g1<<<blocks_for(count, 64), 64, 0, ctx->stream>>>(d_bytes, d_out, d_status, (uint32_t)count, check_subgroup,
+    k_decode_g1<<<blocks_for(count, 64), 64, 0, ctx->cur->stream>>>(d_bytes, d_out, d_status, (uint32_t)count, check_subgroup,
                                                                (uint32_t)status_mod);
     stage_end(ctx, 1);
     ctx->launches++;
@@ -19,26 +19,28 @@ static int decode_points(kzg_b200_ctx *ctx, const uint8_t *d_bytes, g1_affine_t 
 // src/kzg.rs:446-457) is non-null.  d_zy (optional) receives z || y.
 static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments, const uint8_t *d_zbytes,
                        size_t count, uint8_t *d_proofs, uint8_t *d_zy, int32_t *d_status) {
-    CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), ctx->stream));
+    kzg_b200_ctx::Lane *ln = ctx->cur;
+    cudaStream_t st = ln->stream;
+    CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), st));
     if (d_commitments) {
-        RC(decode_points(ctx, d_commitments, ctx->d_pts, d_status, count, 1, count));
+        RC(decode_points(ctx, d_commitments, ln->d_pts, d_status, count, 1, count));
         stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
-        k_challenge<<<blocks_for(count, 64), 64, 0, ctx->stream>>>(d_blobs, d_commitments, (uint32_t)count, ctx->n, ctx->d_z);
+        k_challenge<<<blocks_for(count, 64), 64, 0, st>>>(d_blobs, d_commitments, (uint32_t)count, ctx->n, ln->d_z);
         stage_end(ctx, 1);
     } else {
-        k_load_scalars<<<blocks_for(count, 128), 128, 0, ctx->stream>>>(d_zbytes, (uint32_t)count, ctx->d_z, d_status);
+        k_load_scalars<<<blocks_for(count, 128), 128, 0, st>>>(d_zbytes, (uint32_t)count, ln->d_z, d_status);
     }
     ctx->launches++;
     stage_begin(ctx, KZG_B200_STAGE_EVAL);
-    k_eval_quotient<true><<<(unsigned)count, KZG_EVAL_THREADS, 0, ctx->stream>>>(
-        d_blobs, ctx->d_z, ctx->d_roots, ctx->n, ctx->d_inv, ctx->d_poly, d_zy, ctx->d_digits, ctx->c, ctx->W, d_status);
+    k_eval_quotient<true><<<(unsigned)count, KZG_EVAL_THREADS, 0, st>>>(
+        d_blobs, ln->d_z, ctx->d_roots, ctx->n, ln->d_inv, ln->d_poly, d_zy, ln->d_digits, ctx->c, ctx->W, d_status);
     stage_end(ctx, 1);
     ctx->launches++;
     CU(cudaGetLastError());
     const g1_affine_t *res = nullptr;
     RC(run_msm(ctx, count, &res));
     stage_begin(ctx, KZG_B200_STAGE_COMPRESS);
-    k_horner_compress<<<blocks_for(count, 64), 64, 0, ctx->stream>>>(res, ctx->c, ctx->W, d_status, d_proofs, (uint32_t)count);
+    k_horner_compress<<<blocks_for(count, 64), 64, 0, st>>>(res, ctx->c, ctx->W, d_status, d_proofs, (uint32_t)count);
     stage_end(ctx, 1);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -51,12 +53,15 @@ extern "C" int kzg_b200_compute_blob_kzg_proof_device(kzg_b200_ctx *ctx, const u
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     const size_t bpb = (size_t)ctx->n * 32;
-    for (size_t off = 0; off < n; off += ctx->chunk) {
+    RC(lanes_begin(ctx));
+    size_t i = 0;
+    for (size_t off = 0; off < n; off += ctx->chunk, i++) {
         size_t cnt = std::min(ctx->chunk, n - off);
+        lane_select(ctx, i);
         RC(proof_chunk(ctx, d_blobs + off * bpb, d_commitments + off * 48, nullptr, cnt, d_proofs_out + off * 48, nullptr,
                        d_status + off));
     }
-    return KZG_B200_OK;
+    return lanes_end(ctx);
 }
 
 extern "C" int kzg_b200_compute_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments,
@@ -64,18 +69,22 @@ extern "C" int kzg_b200_compute_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const ui
     if (!ctx || (n && (!blobs || !commitments || !proofs_out || !status))) return KZG_B200_BAD_ARGS;
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(cudaSetDevice(ctx->device));
-    const size_t bpb = (size_t)ctx->n * 32;
-    for (size_t off = 0; off < n; off += ctx->chunk) {
-        size_t cnt = std::min(ctx->chunk, n - off);
-        CU(cudaMemcpyAsync(ctx->d_stage_in, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_stage_aux, commitments + off * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->stream));
-        RC(proof_chunk(ctx, ctx->d_stage_in, ctx->d_stage_aux, nullptr, cnt, ctx->d_stage_out, nullptr, ctx->d_status));
-        CU(cudaMemcpyAsync(proofs_out + off * 48, ctx->d_stage_out, cnt * 48, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(status + off, ctx->d_status, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-    }
-    stage_collect(ctx);
-    return KZG_B200_OK;
+    const size_t bpb = (size_t)ctx->n * 32, ch = ctx->chunk;
+    return staged_chunks(
+        ctx, n,
+        [&](int slot, size_t off, size_t cnt) -> int {
+            CU(cudaMemcpyAsync(ctx->d_stage_in + slot * ch * bpb, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CU(cudaMemcpyAsync(ctx->d_stage_aux + slot * ch * 96, commitments + off * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->copy_stream));
+            return KZG_B200_OK;
+        },
+        [&](int slot, size_t off, size_t cnt) -> int {
+            uint8_t *d_out = ctx->d_stage_out + slot * ch * 96;
+            int32_t *d_st = ctx->d_status + slot * ch;
+            RC(proof_chunk(ctx, ctx->d_stage_in + slot * ch * bpb, ctx->d_stage_aux + slot * ch * 96, nullptr, cnt, d_out, nullptr, d_st));
+            CU(cudaMemcpyAsync(proofs_out + off * 48, d_out, cnt * 48, cudaMemcpyDeviceToHost, ctx->cur->stream));
+            CU(cudaMemcpyAsync(status + off, d_st, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->cur->stream));
+            return KZG_B200_OK;
+        });
 }
 
 extern "C" int kzg_b200_compute_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *z, size_t n,
@@ -83,24 +92,28 @@ extern "C" int kzg_b200_compute_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t
     if (!ctx || (n && (!blobs || !z || !proofs_out || !y_out || !status))) return KZG_B200_BAD_ARGS;
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(cudaSetDevice(ctx->device));
-    const size_t bpb = (size_t)ctx->n * 32;
-    std::vector<uint8_t> zy;
-    for (size_t off = 0; off < n; off += ctx->chunk) {
-        size_t cnt = std::min(ctx->chunk, n - off);
-        zy.resize(cnt * 64);
-        CU(cudaMemcpyAsync(ctx->d_stage_in, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_stage_aux, z + off * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->stream));
-        RC(proof_chunk(ctx, ctx->d_stage_in, nullptr, ctx->d_stage_aux, cnt, ctx->d_stage_out, ctx->d_zy, ctx->d_status));
-        CU(cudaMemcpyAsync(proofs_out + off * 48, ctx->d_stage_out, cnt * 48, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(zy.data(), ctx->d_zy, cnt * 64, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(status + off, ctx->d_status, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        for (size_t i = 0; i < cnt; i++) {
-            if (status[off + i] == KZG_B200_OK) memcpy(y_out + (off + i) * 32, zy.data() + 64 * i + 32, 32);
-            else memset(y_out + (off + i) * 32, 0, 32);
-        }
+    const size_t bpb = (size_t)ctx->n * 32, ch = ctx->chunk;
+    std::vector<uint8_t> zy(n * 64);
+    RC(staged_chunks(
+        ctx, n,
+        [&](int slot, size_t off, size_t cnt) -> int {
+            CU(cudaMemcpyAsync(ctx->d_stage_in + slot * ch * bpb, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CU(cudaMemcpyAsync(ctx->d_stage_aux + slot * ch * 96, z + off * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+            return KZG_B200_OK;
+        },
+        [&](int slot, size_t off, size_t cnt) -> int {
+            uint8_t *d_out = ctx->d_stage_out + slot * ch * 96;
+            int32_t *d_st = ctx->d_status + slot * ch;
+            RC(proof_chunk(ctx, ctx->d_stage_in + slot * ch * bpb, nullptr, ctx->d_stage_aux + slot * ch * 96, cnt, d_out, ctx->cur->d_zy, d_st));
+            CU(cudaMemcpyAsync(proofs_out + off * 48, d_out, cnt * 48, cudaMemcpyDeviceToHost, ctx->cur->stream));
+            CU(cudaMemcpyAsync(zy.data() + off * 64, ctx->cur->d_zy, cnt * 64, cudaMemcpyDeviceToHost, ctx->cur->stream));
+            CU(cudaMemcpyAsync(status + off, d_st, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->cur->stream));
+            return KZG_B200_OK;
+        }));
+    for (size_t i = 0; i < n; i++) {
+        if (status[i] == KZG_B200_OK) memcpy(y_out + i * 32, zy.data() + 64 * i + 32, 32);
+        else memset(y_out + i * 32, 0, 32);
     }
-    stage_collect(ctx);
     return KZG_B200_OK;
 }
 
@@ -108,35 +121,40 @@ extern "C" int kzg_b200_compute_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t
 // Phase A (reference src/kzg.rs:671-683, per blob): validate C_i and proof_i, z_i, y_i.
 static int verify_phase_a_locked(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments, const uint8_t *proofs,
                                  size_t n, uint8_t *zy_out) {
-    const size_t bpb = (size_t)ctx->n * 32;
-    std::vector<int32_t> st;
-    int rc = KZG_B200_OK;
-    for (size_t off = 0; off < n; off += ctx->chunk) {
-        size_t cnt = std::min(ctx->chunk, n - off);
-        st.resize(cnt);
-        CU(cudaMemcpyAsync(ctx->d_stage_in, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_stage_aux, commitments + off * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_stage_aux + cnt * 48, proofs + off * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemsetAsync(ctx->d_status, 0, cnt * sizeof(int32_t), ctx->stream));
-        RC(decode_points(ctx, ctx->d_stage_aux, ctx->d_pts, ctx->d_status, 2 * cnt, 1, cnt));
-        stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
-        k_challenge<<<blocks_for(cnt, 64), 64, 0, ctx->stream>>>(ctx->d_stage_in, ctx->d_stage_aux, (uint32_t)cnt, ctx->n, ctx->d_z);
-        stage_end(ctx, 1);
-        stage_begin(ctx, KZG_B200_STAGE_EVAL);
-        k_eval_quotient<false><<<(unsigned)cnt, KZG_EVAL_THREADS, 0, ctx->stream>>>(
-            ctx->d_stage_in, ctx->d_z, ctx->d_roots, ctx->n, ctx->d_inv, ctx->d_poly, ctx->d_zy, nullptr, ctx->c, ctx->W,
-            ctx->d_status);
-        stage_end(ctx, 1);
-        ctx->launches += 2;
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(zy_out + off * 64, ctx->d_zy, cnt * 64, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(st.data(), ctx->d_status, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        for (size_t i = 0; i < cnt; i++)
-            if (st[i] != KZG_B200_OK) rc = KZG_B200_BAD_ARGS;
-    }
-    stage_collect(ctx);
-    return rc;
+    const size_t bpb = (size_t)ctx->n * 32, ch = ctx->chunk;
+    std::vector<int32_t> st(n);
+    RC(staged_chunks(
+        ctx, n,
+        [&](int slot, size_t off, size_t cnt) -> int {
+            uint8_t *aux = ctx->d_stage_aux + slot * ch * 96;
+            CU(cudaMemcpyAsync(ctx->d_stage_in + slot * ch * bpb, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CU(cudaMemcpyAsync(aux, commitments + off * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CU(cudaMemcpyAsync(aux + cnt * 48, proofs + off * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->copy_stream));
+            return KZG_B200_OK;
+        },
+        [&](int slot, size_t off, size_t cnt) -> int {
+            const uint8_t *d_blobs = ctx->d_stage_in + slot * ch * bpb, *aux = ctx->d_stage_aux + slot * ch * 96;
+            int32_t *d_st = ctx->d_status + slot * ch;
+            kzg_b200_ctx::Lane *ln = ctx->cur;
+            cudaStream_t sm = ln->stream;
+            CU(cudaMemsetAsync(d_st, 0, cnt * sizeof(int32_t), sm));
+            RC(decode_points(ctx, aux, ln->d_pts, d_st, 2 * cnt, 1, cnt));
+            stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
+            k_challenge<<<blocks_for(cnt, 64), 64, 0, sm>>>(d_blobs, aux, (uint32_t)cnt, ctx->n, ln->d_z);
+            stage_end(ctx, 1);
+            stage_begin(ctx, KZG_B200_STAGE_EVAL);
+            k_eval_quotient<false><<<(unsigned)cnt, KZG_EVAL_THREADS, 0, sm>>>(
+                d_blobs, ln->d_z, ctx->d_roots, ctx->n, ln->d_inv, ln->d_poly, ln->d_zy, nullptr, ctx->c, ctx->W, d_st);
+            stage_end(ctx, 1);
+            ctx->launches += 2;
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(zy_out + off * 64, ln->d_zy, cnt * 64, cudaMemcpyDeviceToHost, sm));
+            CU(cudaMemcpyAsync(st.data() + off, d_st, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, sm));
+            return KZG_B200_OK;
+        }));
+    for (size_t i = 0; i < n; i++)
+        if (st[i] != KZG_B200_OK) return KZG_B200_BAD_ARGS;
+    return KZG_B200_OK;
 }
 extern "C" int kzg_b200_verify_phase_a(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments,
                                        const uint8_t *proofs, size_t n, uint8_t *zy_out) {
@@ -185,13 +203,14 @@ static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, 
     fr_t rc;
     scalar_from_be32(rc, r);
     if (!fr_is_canonical(rc)) return KZG_B200_BAD_ARGS;
-    // one allocation: bytes (48 + 48 + 64) n | status 2n | points 2n | terms 2n | tree n + 2 | sy n + 1 | partial
+    ctx->cur = &ctx->lanes[0];
+    // one allocation: bytes (48 + 48 + 64) n | status 2n | points 2n | terms 2n (Jacobian) | sums 2 | sy n + 1 | partial
     const size_t o_c = 0, o_p = o_c + 48 * n, o_zy = o_p + 48 * n;
     size_t o_st = (o_zy + 64 * n + 15) / 16 * 16;
     size_t o_pts = (o_st + 2 * n * sizeof(int32_t) + 15) / 16 * 16;
     size_t o_terms = o_pts + 2 * n * sizeof(g1_affine_t);
-    size_t o_tree = o_terms + 2 * n * sizeof(g1_affine_t);
-    size_t o_sy = o_tree + (n + 2) * sizeof(g1_affine_t);
+    size_t o_sums = o_terms + 2 * n * sizeof(g1_jac_t);
+    size_t o_sy = o_sums + 2 * sizeof(g1_affine_t);
     size_t o_part = o_sy + (n + 1) * sizeof(fr_t);
     size_t total = o_part + 256;
     uint8_t *d = nullptr;
@@ -201,31 +220,19 @@ static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, 
     CU(cudaMemcpyAsync(d + o_p, proofs, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(d + o_zy, zy, 64 * n, cudaMemcpyHostToDevice, ctx->stream));
     int32_t *d_st = (int32_t *)(d + o_st);
-    g1_affine_t *pts = (g1_affine_t *)(d + o_pts), *terms = (g1_affine_t *)(d + o_terms), *tree = (g1_affine_t *)(d + o_tree);
+    g1_affine_t *pts = (g1_affine_t *)(d + o_pts), *sums = (g1_affine_t *)(d + o_sums);
+    g1_jac_t *terms = (g1_jac_t *)(d + o_terms);
     fr_t *sy = (fr_t *)(d + o_sy);
     CU(cudaMemsetAsync(d_st, 0, 2 * n * sizeof(int32_t), ctx->stream));
     // c and p byte arrays are contiguous: decode both with one launch (phase A did the subgroup checks)
     RC(decode_points(ctx, d + o_c, pts, d_st, 2 * n, 0, 2 * n));
     stage_begin(ctx, KZG_B200_STAGE_VERIFY_TERMS);
     k_verify_terms<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(pts, pts + n, d + o_zy, rc, first_index, (uint32_t)n, terms, sy);
-    stage_end(ctx, 1);
-    ctx->launches++;
+    k_jac_sum<<<2, KZG_JSUM_THREADS, 0, ctx->stream>>>(terms, (uint32_t)n, sums);   // sums[0] = sum V_i, sums[1] = sum U_i
+    stage_end(ctx, 2);
+    ctx->launches += 2;
     CU(cudaGetLastError());
-    g1_affine_t *in = terms, *o = tree;
-    size_t cnt = n;
-    // two independent sums (V's, then U's) of cnt points each
-    stage_begin(ctx, KZG_B200_STAGE_MSM_TREE);
-    uint64_t levels = 0;
-    // the ping-pong target must hold 2 * ceil(cnt / 2) points: `tree` for the first level, then `terms`
-    while (cnt > 1) {
-        size_t nxt = (cnt + 1) / 2;
-        TreePolicy tp{in, o, (uint32_t)cnt, (uint32_t)nxt};
-        RC(launch_batch_add(ctx, tp, 2 * (uint64_t)nxt));
-        std::swap(in, o);
-        cnt = nxt;
-        levels++;
-    }
-    stage_end(ctx, levels);
+    const g1_affine_t *in = sums;
     k_fr_sum<<<1, 256, 0, ctx->stream>>>(sy, (uint32_t)n, sy + n);
     k_write_partial<<<1, 32, 0, ctx->stream>>>(in, sy + n, d + o_part);
     ctx->launches += 2;
