@@ -273,8 +273,9 @@ def main():
     verify = None
     if proof is not None and rank == 0:
         nv = min(1024, B)
-        vb = blobs[:nv].reshape(nv, BYTES_PER_BLOB).cpu().numpy()
-        vc, vp = out[:nv].cpu().numpy(), proofs[:nv].cpu().numpy()
+        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t).numpy()
+        vb = pin(blobs[:nv].reshape(nv, BYTES_PER_BLOB))
+        vc, vp = pin(out[:nv]), pin(proofs[:nv])
         verify = {}
         for n_v, reps in ((6, 5), (nv, 2)):
             if not k.Kzg.verify_blob_kzg_proof_batch_raw(vb[:n_v], vc[:n_v], vp[:n_v], n_v, s):

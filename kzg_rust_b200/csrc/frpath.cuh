@@ -309,15 +309,17 @@ __global__ void __launch_bounds__(KZG_EVAL_THREADS) k_eval_quotient(
 
 // ------------------------------------------------------------------ batch verification, phase B
 // Per blob i (global index first + i): r_i = r^(first+i) and the three products
-//   V_i = [r_i] proof_i,   U_i = [r_i] C_i + [r_i z_i] proof_i,   s_i = r_i y_i
+//   V_i = [r_i] proof_i,   U1_i = [r_i] C_i,   U2_i = [r_i z_i] proof_i,   s_i = r_i y_i
 // (reference verify_kzg_proof_batch src/kzg.rs:579-627 and compute_r_powers
 // src/utils.rs:426-474; sum_i r_i [y_i]G is folded into one scalar).
-// Shamir's trick shares the doublings of the two multiplications that make up U_i.
-// out_pts[i] = V_i, out_pts[count + i] = U_i (Jacobian), sy[i] = s_i (Montgomery).
-__global__ void __launch_bounds__(64) k_verify_terms(const g1_affine_t *__restrict__ cpts, const g1_affine_t *__restrict__ ppts,
+// Three threads per blob, one 255-bit double-and-add each (the batch is small and this kernel
+// is latency-bound, so the scalar multiplications run side by side).
+// out[i] = V_i, out[count + 2i] = U1_i, out[count + 2i + 1] = U2_i (Jacobian), sy[i] = s_i.
+__global__ void __launch_bounds__(96) k_verify_terms(const g1_affine_t *__restrict__ cpts, const g1_affine_t *__restrict__ ppts,
                                                      const uint8_t *__restrict__ zy, fr_t r_canon, uint64_t first,
                                                      uint32_t count, g1_jac_t *__restrict__ out_pts, fr_t *__restrict__ sy) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i = t / 3, role = t - 3 * i;
     if (i >= count) return;
     fr_t r, ri = fe_one<FrParams>();
     fe_to_mont(r, r_canon);
@@ -331,42 +333,35 @@ __global__ void __launch_bounds__(64) k_verify_terms(const g1_affine_t *__restri
             e >>= 1;
         }
     }
-    fr_t z, y, t;
-    scalar_from_be32(z, zy + 64ull * i);
-    scalar_from_be32(y, zy + 64ull * i + 32);
-    fe_to_mont(z, z);
-    fe_to_mont(y, y);
-    fe_mul(t, ri, y);
-    st_fr(sy + i, t);
-    fr_t ka, kb;
-    fe_mul(kb, ri, z);
-    fe_from_mont(ka, ri);
-    fe_from_mont(kb, kb);
-    g1_affine_t C = cpts[i], P = ppts[i];
-    const bool c_inf = g1a_is_inf(C), p_inf = g1a_is_inf(P);
-    g1_jac_t V, U;
-    g1j_set_inf(V);
-    g1j_set_inf(U);
-#pragma unroll 1
-    for (int bit = 254; bit >= 0; bit--) {
-        g1j_dbl(V, V);
-        g1j_dbl(U, U);
-        const bool ba = (ka.l[bit >> 5] >> (bit & 31)) & 1, bb = (kb.l[bit >> 5] >> (bit & 31)) & 1;
-        if (ba && !p_inf) g1j_add_affine(V, V, P.x, P.y);
-        if (ba && !c_inf) g1j_add_affine(U, U, C.x, C.y);
-        if (bb && !p_inf) g1j_add_affine(U, U, P.x, P.y);
+    fr_t k = ri;
+    if (role == 0) {
+        fr_t y, s;
+        scalar_from_be32(y, zy + 64ull * i + 32);
+        fe_to_mont(y, y);
+        fe_mul(s, ri, y);
+        st_fr(sy + i, s);
+    } else if (role == 2) {
+        fr_t z;
+        scalar_from_be32(z, zy + 64ull * i);
+        fe_to_mont(z, z);
+        fe_mul(k, ri, z);
     }
-    out_pts[i] = V;
-    out_pts[count + i] = U;
+    fe_from_mont(k, k);
+    const g1_affine_t base_pt = role == 1 ? cpts[i] : ppts[i];
+    g1_jac_t acc;
+    g1j_mul(acc, base_pt, k.l, 255);
+    out_pts[role == 0 ? i : count + 2 * i + (role - 1)] = acc;
 }
-// block b adds the `count` Jacobian points pts[b*count ..] -> out[b] (affine): strided partial
+// Each block adds a run of Jacobian points -> out[block] (affine): strided partial
 // sums per thread, then a shared-memory tree.  The sums of batch verification are a few
 // thousand points at most, so one block each beats a log-depth chain of launches.
 #define KZG_JSUM_THREADS 128
-__global__ void __launch_bounds__(KZG_JSUM_THREADS) k_jac_sum(const g1_jac_t *__restrict__ pts, uint32_t count,
+// block 0 sums pts[0, count), block 1 sums pts[count, 3 count)
+__global__ void __launch_bounds__(KZG_JSUM_THREADS) k_jac_sum(const g1_jac_t *__restrict__ pts, uint32_t count0,
                                                               g1_affine_t *__restrict__ out) {
     __shared__ g1_jac_t red[KZG_JSUM_THREADS];
-    const g1_jac_t *base = pts + (size_t)blockIdx.x * count;
+    const g1_jac_t *base = pts + (blockIdx.x ? count0 : 0);
+    const uint32_t count = blockIdx.x ? 2 * count0 : count0;
     g1_jac_t acc;
     g1j_set_inf(acc);
 #pragma unroll 1

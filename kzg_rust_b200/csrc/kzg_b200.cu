@@ -47,6 +47,8 @@ struct kzg_b200_ctx {
     int sms = 0;
     int max_k = 4096; // additions per thread per batch (one shared inversion per block and batch)
     int add_blocks = 3;  // resident blocks per SM of the addition kernel (KZG_B200_ADD_BLOCKS)
+    int grid_mult = 1;   // grid = grid_mult x grid_blocks x SMs (KZG_B200_GRID_MULT)
+    int grid_blocks = 3; // blocks per SM a launch asks for (KZG_B200_GRID_BLOCKS); below add_blocks leaves room for the other lane
     g1_affine_t *d_table = nullptr;
     fr_t *d_roots = nullptr;       // roots of unity, Montgomery form, bit-reversed (src/kzg.rs:764-799)
     uint8_t g2_tau[96];            // [tau]G2 = g2_values[1]
@@ -81,6 +83,8 @@ struct kzg_b200_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_h2d[KZG_SLOTS] = {nullptr, nullptr, nullptr}, ev_free[KZG_SLOTS] = {nullptr, nullptr, nullptr};
     host_g2_prepared *tau_prepared = nullptr;  // Miller-loop lines of [tau]G2
+    uint8_t *d_vb = nullptr;          // phase-B buffer of batch verification (grow-only)
+    size_t vb_bytes = 0;
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
     // optional per-stage device timing (CUDA events on `stream`), see kzg_b200_profile_*
@@ -255,7 +259,7 @@ template <class Policy>
 static int launch_batch_add(kzg_b200_ctx *ctx, const Policy &pol, uint64_t total) {
     if (total == 0) return KZG_B200_OK;
     const unsigned tpb = KZG_ADD_THREADS;
-    const uint64_t t_max = (uint64_t)ctx->sms * ctx->add_blocks * tpb;
+    const uint64_t t_max = (uint64_t)ctx->sms * ctx->grid_blocks * tpb * ctx->grid_mult;
     uint64_t T;
     int k;
     if (total <= t_max) {
@@ -422,6 +426,8 @@ extern "C" int kzg_b200_ctx_create(const uint8_t *g1_lagrange, size_t n1, const 
     ctx->sms = prop.multiProcessorCount;
     ctx->max_k = env_int("KZG_B200_BATCH_K", 4096);
     ctx->add_blocks = env_int("KZG_B200_ADD_BLOCKS", 3) >= 4 ? 4 : 3;
+    ctx->grid_mult = std::max(1, env_int("KZG_B200_GRID_MULT", 1));
+    ctx->grid_blocks = std::max(1, env_int("KZG_B200_GRID_BLOCKS", ctx->add_blocks));
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KZG_B200_CUDA_ERROR; }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { kzg_b200_ctx_destroy(ctx); return KZG_B200_CUDA_ERROR; }
     ctx->nlanes = env_int("KZG_B200_LANES", 2) >= 2 ? 2 : 1;
@@ -509,6 +515,7 @@ extern "C" void kzg_b200_ctx_destroy(kzg_b200_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->lanes[1].stream) cudaStreamSynchronize(ctx->lanes[1].stream);
     free_workspace(ctx);
+    cudaFree(ctx->d_vb);
     cudaFree(ctx->d_table);
     cudaFree(ctx->d_roots);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -204,18 +204,23 @@ static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, 
     scalar_from_be32(rc, r);
     if (!fr_is_canonical(rc)) return KZG_B200_BAD_ARGS;
     ctx->cur = &ctx->lanes[0];
-    // one allocation: bytes (48 + 48 + 64) n | status 2n | points 2n | terms 2n (Jacobian) | sums 2 | sy n + 1 | partial
+    // one buffer: bytes (48 + 48 + 64) n | status 2n | points 2n | terms 3n (Jacobian) | sums 2 | sy n + 1 | partial
     const size_t o_c = 0, o_p = o_c + 48 * n, o_zy = o_p + 48 * n;
     size_t o_st = (o_zy + 64 * n + 15) / 16 * 16;
     size_t o_pts = (o_st + 2 * n * sizeof(int32_t) + 15) / 16 * 16;
     size_t o_terms = o_pts + 2 * n * sizeof(g1_affine_t);
-    size_t o_sums = o_terms + 2 * n * sizeof(g1_jac_t);
+    size_t o_sums = o_terms + 3 * n * sizeof(g1_jac_t);
     size_t o_sy = o_sums + 2 * sizeof(g1_affine_t);
     size_t o_part = o_sy + (n + 1) * sizeof(fr_t);
     size_t total = o_part + 256;
-    uint8_t *d = nullptr;
-    CU(cudaMalloc(&d, total));
-    struct Free { uint8_t *p; ~Free() { cudaFree(p); } } guard{d};
+    if (total > ctx->vb_bytes) {  // grow-only buffer kept by the context
+        if (ctx->d_vb) CU(cudaFree(ctx->d_vb));
+        ctx->d_vb = nullptr;
+        ctx->vb_bytes = 0;
+        CU(cudaMalloc(&ctx->d_vb, total + total / 2));
+        ctx->vb_bytes = total + total / 2;
+    }
+    uint8_t *d = ctx->d_vb;
     CU(cudaMemcpyAsync(d + o_c, commitments, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(d + o_p, proofs, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(d + o_zy, zy, 64 * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -227,7 +232,7 @@ static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, 
     // c and p byte arrays are contiguous: decode both with one launch (phase A did the subgroup checks)
     RC(decode_points(ctx, d + o_c, pts, d_st, 2 * n, 0, 2 * n));
     stage_begin(ctx, KZG_B200_STAGE_VERIFY_TERMS);
-    k_verify_terms<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(pts, pts + n, d + o_zy, rc, first_index, (uint32_t)n, terms, sy);
+    k_verify_terms<<<blocks_for(3 * n, 96), 96, 0, ctx->stream>>>(pts, pts + n, d + o_zy, rc, first_index, (uint32_t)n, terms, sy);
     k_jac_sum<<<2, KZG_JSUM_THREADS, 0, ctx->stream>>>(terms, (uint32_t)n, sums);   // sums[0] = sum V_i, sums[1] = sum U_i
     stage_end(ctx, 2);
     ctx->launches += 2;

@@ -83,7 +83,18 @@ struct Sha256 {
         }
     }
     KZG_HD void update(const uint8_t *p, size_t n) {
-        for (size_t i = 0; i < n; i++) put_byte(p[i]);
+        size_t i = 0;
+        while (i < n && (len & 63) != 0) put_byte(p[i++]);
+        for (; i + 64 <= n; i += 64) {  // whole blocks straight from the input
+            uint32_t t[16];
+            for (int k = 0; k < 16; k++) {
+                const uint8_t *q = p + i + 4 * k;
+                t[k] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+            }
+            sha256_compress(h, t);
+            len += 64;
+        }
+        for (; i < n; i++) put_byte(p[i]);
     }
     KZG_HD void finish(uint8_t out[32]) {
         uint64_t bits = len * 8;
