@@ -44,7 +44,8 @@ KZG_CONST_TABLE(fp_p_minus_1_div_2, FP_P_MINUS_1_DIV_2_LIMBS)
 KZG_CONST_TABLE(fr_r_minus_2, FR_R_MINUS_2_LIMBS)
 
 // ---- Fp helpers
-KZG_HD void fp_inv(fp_t &r, const fp_t &a) { fe_pow(r, a, KZG_TABLE(fp_p_minus_2), 12); }
+KZG_HD void fp_inv(fp_t &r, const fp_t &a) { fe_inv_binary(r, a); }
+KZG_HD void fp_inv_fermat(fp_t &r, const fp_t &a) { fe_pow(r, a, KZG_TABLE(fp_p_minus_2), 12); }
 // sqrt for p = 3 (mod 4): candidate a^((p+1)/4); false when a is not a square
 KZG_HD bool fp_sqrt(fp_t &r, const fp_t &a) {
     fp_t s, s2;
@@ -71,7 +72,8 @@ KZG_HD fp_t fp_const_b() { fp_t r; constexpr uint32_t v[12] = {FP_B_MONT_LIMBS};
     return r; }
 
 // ---- Fr helpers
-KZG_HD void fr_inv(fr_t &r, const fr_t &a) { fe_pow(r, a, KZG_TABLE(fr_r_minus_2), 8); }
+KZG_HD void fr_inv(fr_t &r, const fr_t &a) { fe_inv_binary(r, a); }
+KZG_HD void fr_inv_fermat(fr_t &r, const fr_t &a) { fe_pow(r, a, KZG_TABLE(fr_r_minus_2), 8); }
 // 32 big-endian bytes (as 8 big-endian words already byte-swapped to host order, most
 // significant first) -> canonical little-endian limbs
 KZG_HD bool fr_is_canonical(const fr_t &a) {

@@ -13,6 +13,8 @@ void shim_fr_mul(const uint32_t *a, const uint32_t *b, uint32_t *r) { fr_t x, y,
 void shim_fr_add(const uint32_t *a, const uint32_t *b, uint32_t *r) { fr_t x, y, z; memcpy(x.l, a, 32); memcpy(y.l, b, 32); fe_add(z, x, y); memcpy(r, z.l, 32); }
 void shim_fr_sub(const uint32_t *a, const uint32_t *b, uint32_t *r) { fr_t x, y, z; memcpy(x.l, a, 32); memcpy(y.l, b, 32); fe_sub(z, x, y); memcpy(r, z.l, 32); }
 void shim_fr_inv(const uint32_t *a, uint32_t *r) { fr_t x, z; memcpy(x.l, a, 32); fr_inv(z, x); memcpy(r, z.l, 32); }
+void shim_fp_inv_fermat(const uint32_t *a, uint32_t *r) { fp_t x, z; memcpy(x.l, a, 48); fp_inv_fermat(z, x); memcpy(r, z.l, 48); }
+void shim_fr_inv_fermat(const uint32_t *a, uint32_t *r) { fr_t x, z; memcpy(x.l, a, 32); fr_inv_fermat(z, x); memcpy(r, z.l, 32); }
 int shim_fr_canonical(const uint32_t *a) { fr_t x; memcpy(x.l, a, 32); return fr_is_canonical(x); }
 }
 extern "C" {

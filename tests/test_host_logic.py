@@ -67,9 +67,11 @@ def test_fp_and_fr_arithmetic_vs_python(field):
         assert _val(out) == (a + b) % P
         field.shim_fp_sub(_limbs(a, 12), _limbs(b, 12), out)
         assert _val(out) == (a - b) % P
-    for a in vals_p[1:20]:
+    for a in vals_p[1:60]:
         am = a * Rp % P
-        field.shim_fp_inv(_limbs(am, 12), out)
+        field.shim_fp_inv(_limbs(am, 12), out)          # binary extended Euclid
+        assert _val(out) == pow(a, -1, P) * Rp % P
+        field.shim_fp_inv_fermat(_limbs(am, 12), out)   # a^(p-2)
         assert _val(out) == pow(a, -1, P) * Rp % P
         sq = a * a % P
         ok = field.shim_fp_sqrt(_limbs(sq * Rp % P, 12), out)
@@ -87,8 +89,10 @@ def test_fp_and_fr_arithmetic_vs_python(field):
         assert _val(out8) == (a + b) % R
         field.shim_fr_sub(_limbs(a, 8), _limbs(b, 8), out8)
         assert _val(out8) == (a - b) % R
-    for a in vals_r[1:12]:
+    for a in vals_r[1:60]:
         field.shim_fr_inv(_limbs(a * Rr % R, 8), out8)
+        assert _val(out8) == pow(a, -1, R) * Rr % R
+        field.shim_fr_inv_fermat(_limbs(a * Rr % R, 8), out8)
         assert _val(out8) == pow(a, -1, R) * Rr % R
     assert field.shim_fr_canonical(_limbs(R - 1, 8)) and not field.shim_fr_canonical(_limbs(R, 8))
     assert not field.shim_fr_canonical(_limbs(2 ** 256 - 1, 8))
