@@ -107,15 +107,16 @@ KZG_HD void fr_digits_thread(const fr_t *evals, uint64_t e, int n, int c, int W,
 }
 
 // Horner pass over the W window sums of one blob: sum_j 2^(c j) S_j, S_j affine (possibly
-// infinity) at sums[j].  (W-1)(c doublings + 1 mixed addition) in Jacobian coordinates.
-KZG_HD void horner_thread(g1_affine_t &out, const g1_affine_t *sums, int c, int W) {
+// infinity) at sums[j*stride] (the MSM leaves them window-major: stride = blobs in the chunk).
+// (W-1)(c doublings + 1 mixed addition) in Jacobian coordinates.
+KZG_HD void horner_thread(g1_affine_t &out, const g1_affine_t *sums, size_t stride, int c, int W) {
     g1_jac_t acc;
-    g1j_from_affine(acc, sums[W - 1]);
+    g1j_from_affine(acc, sums[(size_t)(W - 1) * stride]);
 #pragma unroll 1
     for (int j = W - 2; j >= 0; j--) {
 #pragma unroll 1
         for (int k = 0; k < c; k++) g1j_dbl(acc, acc);
-        g1_affine_t s = sums[j];
+        g1_affine_t s = sums[(size_t)j * stride];
         if (!g1a_is_inf(s)) g1j_add_affine(acc, acc, s.x, s.y);
     }
     g1j_to_affine(out, acc);

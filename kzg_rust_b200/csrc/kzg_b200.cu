@@ -59,7 +59,8 @@ struct kzg_b200_ctx {
     // (calls on a context are serialised by `mu`).
     struct Lane {
         cudaStream_t stream = nullptr;
-        int32_t *d_digits = nullptr;
+        int32_t *d_digits = nullptr;      // [b][j][i] as the per-blob kernels write them
+        int32_t *d_digits_t = nullptr;    // [i][j][b] point-major copy the gather level reads
         g1_affine_t *d_buf_a = nullptr, *d_buf_b = nullptr;
         fp_t *d_scratch = nullptr;
         size_t scratch_elems = 0;
@@ -157,7 +158,24 @@ __global__ void k_fr_digits(const fr_t *evals, uint64_t total, int n, int c, int
     if (e >= total) return;
     fr_digits_thread(evals, e, n, c, W, digits);
 }
-// window sums of blob i (W affine points) -> Horner -> 48-byte compressed point
+// digits[(b*W + j)*n + i] (as the per-blob producers write them, coalesced in i)
+//   -> digits_t[(i*W + j)*count + b] (point-major, what the gather level reads, coalesced in b)
+// grid (n/32, ceil(count/32), W), block (32, 8)
+__global__ void k_transpose_digits(const int32_t *__restrict__ in, int32_t *__restrict__ out, uint32_t n, uint32_t W,
+                                   uint32_t count) {
+    __shared__ int32_t tile[32][33];
+    const uint32_t j = blockIdx.z, i0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+    for (uint32_t r = threadIdx.y; r < 32; r += 8) {
+        uint32_t b = b0 + r, i = i0 + threadIdx.x;
+        if (b < count && i < n) tile[r][threadIdx.x] = in[((uint64_t)b * W + j) * n + i];
+    }
+    __syncthreads();
+    for (uint32_t r = threadIdx.y; r < 32; r += 8) {
+        uint32_t i = i0 + r, b = b0 + threadIdx.x;
+        if (b < count && i < n) out[((uint64_t)i * W + j) * count + b] = tile[threadIdx.x][r];
+    }
+}
+// window sums of blob i (W affine points at sums[j*count + i]) -> Horner -> 48-byte compressed point
 __global__ void __launch_bounds__(64) k_horner_compress(const g1_affine_t *sums, int c, int W, const int32_t *status, uint8_t *out,
                                                         uint32_t count) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,7 +185,7 @@ __global__ void __launch_bounds__(64) k_horner_compress(const g1_affine_t *sums,
         for (int k = 0; k < 48; k++) buf[k] = 0;
     } else {
         g1_affine_t p;
-        horner_thread(p, sums + (size_t)i * W, c, W);
+        horner_thread(p, sums + i, count, c, W);
         g1a_compress(buf, p);
     }
     uint32_t *o = reinterpret_cast<uint32_t *>(out + 48ull * i);
@@ -280,24 +298,35 @@ static int launch_batch_add(kzg_b200_ctx *ctx, const Policy &pol, uint64_t total
     return KZG_B200_OK;
 }
 
-// the W window sums (4096 table entries each, selected by d_digits) of `count` blobs:
-// (*out)[b*W + j] = S_j of blob b
+// the W window sums (4096 table entries each, selected by d_digits) of `count` blobs, window-major:
+// (*out)[j*count + b] = S_j of blob b
 static int run_msm(kzg_b200_ctx *ctx, size_t count, const g1_affine_t **out) {
-    uint32_t per_blob = (uint32_t)ctx->W * ctx->n, cnt = per_blob / 2;
     kzg_b200_ctx::Lane *ln = ctx->cur;
-    GatherPolicy gp{ctx->d_table, ln->d_digits, ln->d_buf_a, per_blob, (uint32_t)ctx->n - 1, ctx->D};
+    const uint32_t n = (uint32_t)ctx->n, W = (uint32_t)ctx->W;
+    const uint64_t R = (uint64_t)count * W;  // (window, blob) pairs = points per row of a level
+    if (R * (n / 2) >= (1ull << 32)) return KZG_B200_BAD_ARGS;  // chunk sizes keep every level below 2^32 additions
+    stage_begin(ctx, KZG_B200_STAGE_DIGITS);
+    {
+        dim3 grid((n + 31) / 32, (unsigned)((count + 31) / 32), W), block(32, 8);
+        k_transpose_digits<<<grid, block, 0, ln->stream>>>(ln->d_digits, ln->d_digits_t, n, W, (uint32_t)count);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    stage_end(ctx, 1);
+    const FastDiv fd = FastDiv::make((uint32_t)R);
+    uint32_t rows = n / 2;
+    GatherPolicy gp{ctx->d_table, ln->d_digits_t, ln->d_buf_a, fd, ctx->D};
     stage_begin(ctx, KZG_B200_STAGE_MSM_GATHER);
-    RC(launch_batch_add(ctx, gp, (uint64_t)count * cnt));
+    RC(launch_batch_add(ctx, gp, R * rows));
     stage_end(ctx, 1);
     g1_affine_t *in = ln->d_buf_a, *o = ln->d_buf_b;
     stage_begin(ctx, KZG_B200_STAGE_MSM_TREE);
     uint64_t levels = 0;
-    while (cnt > (uint32_t)ctx->W) {  // n is a power of two: pairs never straddle two windows
-        uint32_t nxt = cnt / 2;
-        PairPolicy tp{in, o};
-        RC(launch_batch_add(ctx, tp, (uint64_t)count * nxt));
+    while (rows > 1) {
+        rows /= 2;
+        PairPolicy tp{in, o, fd};
+        RC(launch_batch_add(ctx, tp, R * rows));
         std::swap(in, o);
-        cnt = nxt;
         levels++;
     }
     stage_end(ctx, levels);
@@ -308,16 +337,16 @@ static int run_msm(kzg_b200_ctx *ctx, size_t count, const g1_affine_t **out) {
 // ------------------------------------------------------------------ workspace
 static size_t per_blob_workspace(const kzg_b200_ctx *ctx) {
     size_t wn = (size_t)ctx->W * ctx->n;
-    size_t lane = wn * 4 /*digits*/ + wn / 2 * sizeof(g1_affine_t) + (wn / 4 + 1) * sizeof(g1_affine_t) +
+    size_t lane = 2 * wn * 4 /*digits, both layouts*/ + wn / 2 * sizeof(g1_affine_t) + (wn / 4 + 1) * sizeof(g1_affine_t) +
                   2 * (size_t)ctx->n * sizeof(fr_t) /*poly, inv*/ + 64 + sizeof(fr_t) + 2 * sizeof(g1_affine_t) +
                   (wn / 2) * sizeof(fp_t) /*scratch of the gather level*/;
     return ctx->nlanes * lane + KZG_SLOTS * ((size_t)ctx->n * 32 + 96 * 2 + 4);
 }
 static void free_workspace(kzg_b200_ctx *ctx) {
     for (auto &ln : ctx->lanes) {
-        cudaFree(ln.d_digits); cudaFree(ln.d_buf_a); cudaFree(ln.d_buf_b); cudaFree(ln.d_poly); cudaFree(ln.d_inv);
+        cudaFree(ln.d_digits); cudaFree(ln.d_digits_t); cudaFree(ln.d_buf_a); cudaFree(ln.d_buf_b); cudaFree(ln.d_poly); cudaFree(ln.d_inv);
         cudaFree(ln.d_z); cudaFree(ln.d_zy); cudaFree(ln.d_pts); cudaFree(ln.d_scratch);
-        ln.d_digits = nullptr; ln.d_buf_a = ln.d_buf_b = nullptr; ln.d_poly = ln.d_inv = ln.d_z = nullptr;
+        ln.d_digits = ln.d_digits_t = nullptr; ln.d_buf_a = ln.d_buf_b = nullptr; ln.d_poly = ln.d_inv = ln.d_z = nullptr;
         ln.d_zy = nullptr; ln.d_pts = nullptr; ln.d_scratch = nullptr; ln.scratch_elems = 0;
     }
     cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_aux); cudaFree(ctx->d_stage_out); cudaFree(ctx->d_status);
@@ -331,6 +360,7 @@ static int alloc_workspace(kzg_b200_ctx *ctx, size_t chunk) {
     for (int l = 0; l < ctx->nlanes; l++) {
         kzg_b200_ctx::Lane &ln = ctx->lanes[l];
         CU(cudaMalloc(&ln.d_digits, chunk * wn * sizeof(int32_t)));
+        CU(cudaMalloc(&ln.d_digits_t, chunk * wn * sizeof(int32_t)));
         CU(cudaMalloc(&ln.d_buf_a, chunk * (wn / 2) * sizeof(g1_affine_t)));
         CU(cudaMalloc(&ln.d_buf_b, chunk * (wn / 4 + 1) * sizeof(g1_affine_t)));
         CU(cudaMalloc(&ln.d_poly, chunk * (size_t)ctx->n * sizeof(fr_t)));

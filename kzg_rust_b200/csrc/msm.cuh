@@ -51,14 +51,44 @@ KZG_HD void st_fp(fp_t *p, const fp_t &r) {
 // A policy maps the flat addition index g to two source points (nullptr = infinity, with
 // an optional negation of y) and one destination.
 
-// Level >= 1 of the tree when every group has an even number of points (always true for the
-// window sums: n is a power of two): out[g] = in[2g] + in[2g+1], no index arithmetic.
+// Division of a 32-bit index by a launch constant (the rows-per-point count R below) without a
+// divide: q = floor(g * ceil(2^64 / d) / 2^64) is exact for g, d < 2^32.
+struct FastDiv {
+    uint64_t magic;
+    uint32_t d;
+    static FastDiv make(uint32_t d) {
+        FastDiv f;
+        f.d = d;
+        f.magic = d > 1 ? ~0ull / d + 1 : 0;  // ceil(2^64 / d) (d does not divide 2^64 unless it is a power of two: +1 is still exact)
+        return f;
+    }
+    KZG_HD uint32_t div(uint32_t g) const {
+        if (d == 1) return g;
+#if defined(__CUDA_ARCH__)
+        return (uint32_t)__umul64hi((uint64_t)g, magic);
+#else
+        return (uint32_t)(((unsigned __int128)g * magic) >> 64);
+#endif
+    }
+};
+
+// The window sums run in a POINT-MAJOR layout: a level holds `rows` rows of R = (blobs in the
+// chunk) x W points, row q of level L being the partial sums over points [q 2^L, (q+1) 2^L) of
+// every (window, blob) pair:  level[q*R + (j*count + b)].  Adjacent threads work on adjacent
+// (window, blob) pairs of the SAME point pair, so at any moment the whole GPU reads the table
+// rows of a handful of points (2^(c-1) x 96 B = 25 MB each at c = 19) instead of scattering over
+// the whole 100 GB table -- DRAM pages and TLB entries are reused -- and every load and store of
+// the tree levels is coalesced.
+//
+// Level >= 1: out[q*R + r] = in[2q*R + r] + in[(2q+1)*R + r]
 struct PairPolicy {
     const g1_affine_t *in;
     g1_affine_t *out;
+    FastDiv R;
     KZG_HD const g1_affine_t *src(uint64_t g, int which, bool &neg) const {
         neg = false;
-        return in + 2 * g + which;
+        uint32_t q = R.div((uint32_t)g);
+        return in + g + (uint64_t)(q + (uint32_t)which) * R.d;
     }
     KZG_HD g1_affine_t *dst(uint64_t g) const { return out + g; }
 };
@@ -80,23 +110,22 @@ struct TreePolicy {
 };
 
 // Level 0: operands are table entries selected by the signed digits of the scalars.
-//   digits[(b*W + j)*n + i]  (int32, |d| <= D); n is a power of two
+//   digits[(i*W + j)*count + b]  (int32, |d| <= D), point-major like the levels above:
+//   out[p*R + r] = sign * table[2p][|d(2p, r)|] + sign * table[2p+1][|d(2p+1, r)|],  r = j*count + b
 struct GatherPolicy {
     const g1_affine_t *table;
     const int32_t *digits;
     g1_affine_t *out;
-    uint32_t per_blob;  // W*n
-    uint32_t n_mask;    // n - 1
+    FastDiv R;
     uint32_t D;
-    // operand `which` of addition g is element 2g + which of the flat (blob, window, point)
-    // digit array; per_blob is a multiple of n, so the point index is its low bits
     KZG_HD const g1_affine_t *src(uint64_t g, int which, bool &neg) const {
-        uint64_t idx = 2 * g + which;
-        int d = digits[idx];
+        uint32_t p = R.div((uint32_t)g);
+        uint32_t i = 2 * p + (uint32_t)which;
+        int d = digits[g + (uint64_t)(p + (uint32_t)which) * R.d];  // = i*R + r
         neg = d < 0;
         if (d == 0) return nullptr;
         uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
-        return table + ((uint64_t)((uint32_t)idx & n_mask) * D + (mag - 1));
+        return table + ((uint64_t)i * D + (mag - 1));
     }
     KZG_HD g1_affine_t *dst(uint64_t g) const { return out + g; }
 };

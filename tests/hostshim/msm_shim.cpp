@@ -38,21 +38,27 @@ extern "C" int shim_commit(const uint8_t *g1_bytes, int n, int c, const uint8_t 
     std::vector<int32_t> digits((size_t)B * W * n);
     for (int b = 0; b < B; b++) status[b] = 0;
     for (uint64_t e = 0; e < (uint64_t)B * n; e++) blob_digits_thread(blobs, e, n, c, W, digits.data(), status);
-    uint32_t per_blob = W * n, cnt = per_blob / 2;
-    std::vector<g1_affine_t> a((size_t)B * cnt), b2((size_t)B * cnt);
-    GatherPolicy gp{table.data(), digits.data(), a.data(), per_blob, (uint32_t)n - 1, D};
-    run_level(gp, (uint64_t)B * cnt, T, k);
+    // point-major copy of the digits (k_transpose_digits on the device)
+    std::vector<int32_t> digits_t((size_t)B * W * n);
+    for (int b = 0; b < B; b++)
+        for (int j = 0; j < W; j++)
+            for (int i = 0; i < n; i++) digits_t[((size_t)i * W + j) * B + b] = digits[((size_t)b * W + j) * n + i];
+    const uint64_t R = (uint64_t)B * W;
+    const FastDiv fd = FastDiv::make((uint32_t)R);
+    uint32_t rows = n / 2;
+    std::vector<g1_affine_t> a((size_t)R * rows), b2((size_t)R * rows);
+    GatherPolicy gp{table.data(), digits_t.data(), a.data(), fd, D};
+    run_level(gp, R * rows, T, k);
     g1_affine_t *in = a.data(), *o = b2.data();
-    while (cnt > (uint32_t)W) {
-        uint32_t nxt = cnt / 2;
-        PairPolicy tp{in, o};
-        run_level(tp, (uint64_t)B * nxt, T, k);
+    while (rows > 1) {
+        rows /= 2;
+        PairPolicy tp{in, o, fd};
+        run_level(tp, R * rows, T, k);
         std::swap(in, o);
-        cnt = nxt;
     }
     for (int b = 0; b < B; b++) {
         g1_affine_t p;
-        horner_thread(p, in + (size_t)b * W, c, W);
+        horner_thread(p, in + b, (size_t)B, c, W);
         g1a_compress(out + 48 * b, p);
     }
     return 0;
