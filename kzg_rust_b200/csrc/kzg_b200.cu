@@ -38,6 +38,7 @@ using namespace kzg;
 
 // ------------------------------------------------------------------ context
 #define KZG_SLOTS 3
+#define KZG_DYN_COUNTERS 32
 struct kzg_b200_ctx {
     int device = 0;
     int n = 0;        // FIELD_ELEMENTS_PER_BLOB
@@ -48,6 +49,9 @@ struct kzg_b200_ctx {
     int max_k = 4096; // additions per thread per batch (one shared inversion per block and batch)
     int add_blocks = 3;  // resident blocks per SM of the addition kernel (KZG_B200_ADD_BLOCKS)
     int grid_mult = 1;   // grid = grid_mult x grid_blocks x SMs (KZG_B200_GRID_MULT)
+    int tree_blocks = 0; // blocks per SM of the tree levels of the MSM (KZG_B200_TREE_BLOCKS; 0 = grid_blocks). 2 is 5% faster per launch but loses the overlap of the two lanes
+    bool dynamic = false; // KZG_B200_DYNAMIC=1: MSM levels pull 32-addition tiles from a counter instead of equal static shares
+    int dyn_min_batch = 32;  // shortest batch (tiles per inversion) at the end of a work-pulling launch (KZG_B200_DYN_MIN_BATCH)
     int grid_blocks = 3; // blocks per SM a launch asks for (KZG_B200_GRID_BLOCKS); below add_blocks leaves room for the other lane
     g1_affine_t *d_table = nullptr;
     fr_t *d_roots = nullptr;       // roots of unity, Montgomery form, bit-reversed (src/kzg.rs:764-799)
@@ -61,6 +65,7 @@ struct kzg_b200_ctx {
         cudaStream_t stream = nullptr;
         int32_t *d_digits = nullptr;      // [b][j][i] as the per-blob kernels write them
         int32_t *d_digits_t = nullptr;    // [i][j][b] point-major copy the gather level reads
+        unsigned int *d_counters = nullptr;  // tile counters of the work-pulling launches, one per level
         g1_affine_t *d_buf_a = nullptr, *d_buf_b = nullptr;
         fp_t *d_scratch = nullptr;
         size_t scratch_elems = 0;
@@ -273,11 +278,12 @@ static int ensure_scratch(kzg_b200_ctx *ctx, size_t elems) {
     return KZG_B200_OK;
 }
 
+// blocks_per_sm = 0: the context's default (grid_blocks)
 template <class Policy>
-static int launch_batch_add(kzg_b200_ctx *ctx, const Policy &pol, uint64_t total) {
+static int launch_batch_add(kzg_b200_ctx *ctx, const Policy &pol, uint64_t total, int blocks_per_sm = 0) {
     if (total == 0) return KZG_B200_OK;
     const unsigned tpb = KZG_ADD_THREADS;
-    const uint64_t t_max = (uint64_t)ctx->sms * ctx->grid_blocks * tpb * ctx->grid_mult;
+    const uint64_t t_max = (uint64_t)ctx->sms * (blocks_per_sm > 0 ? blocks_per_sm : ctx->grid_blocks) * tpb * ctx->grid_mult;
     uint64_t T;
     int k;
     if (total <= t_max) {
@@ -293,6 +299,35 @@ static int launch_batch_add(kzg_b200_ctx *ctx, const Policy &pol, uint64_t total
         batch_add_kernel<Policy, 4><<<(unsigned)(T / tpb), tpb, 0, ctx->cur->stream>>>(pol, total, ctx->cur->d_scratch, k);
     else
         batch_add_kernel<Policy, 3><<<(unsigned)(T / tpb), tpb, 0, ctx->cur->stream>>>(pol, total, ctx->cur->d_scratch, k);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return KZG_B200_OK;
+}
+
+// Work-pulling launch (batch_add_dyn_kernel): warps take 32-addition tiles from counter #slot of the lane.
+template <class Policy>
+static int launch_batch_add_dyn(kzg_b200_ctx *ctx, const Policy &pol, uint64_t total, int slot) {
+    if (total == 0) return KZG_B200_OK;
+    kzg_b200_ctx::Lane *ln = ctx->cur;
+    const unsigned tpb = KZG_ADD_THREADS;
+    const uint64_t ntiles = (total + 31) / 32;
+    uint64_t blocks = (uint64_t)ctx->sms * ctx->grid_blocks;
+    blocks = std::min<uint64_t>(blocks, (ntiles + tpb / 32 - 1) / (tpb / 32));
+    const uint64_t nwarps = blocks * (tpb / 32);
+    DynSchedule ds;
+    ds.ntiles = (uint32_t)ntiles;
+    ds.m_min = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(ntiles / (nwarps * 8), 1), (uint64_t)ctx->dyn_min_batch);
+    ds.cap = (uint32_t)std::max<uint64_t>(ntiles / (2 * nwarps) + 1, ds.m_min);
+    const size_t prefix_elems = (size_t)nwarps * ds.cap * 32;
+    const size_t id_elems = ((size_t)nwarps * ds.cap * sizeof(uint32_t) + sizeof(fp_t) - 1) / sizeof(fp_t);
+    RC(ensure_scratch(ctx, prefix_elems + id_elems));
+    ds.scratch = ln->d_scratch;
+    ds.tile_ids = reinterpret_cast<uint32_t *>(ln->d_scratch + prefix_elems);
+    ds.counter = ln->d_counters + slot;
+    if (ctx->add_blocks >= 4)
+        batch_add_dyn_kernel<Policy, 4><<<(unsigned)blocks, tpb, 0, ln->stream>>>(pol, total, ds);
+    else
+        batch_add_dyn_kernel<Policy, 3><<<(unsigned)blocks, tpb, 0, ln->stream>>>(pol, total, ds);
     ctx->launches++;
     CU(cudaGetLastError());
     return KZG_B200_OK;
@@ -315,9 +350,12 @@ static int run_msm(kzg_b200_ctx *ctx, size_t count, const g1_affine_t **out) {
     stage_end(ctx, 1);
     const FastDiv fd = FastDiv::make((uint32_t)R);
     uint32_t rows = n / 2;
+    int slot = 0;
+    if (ctx->dynamic) CU(cudaMemsetAsync(ln->d_counters, 0, KZG_DYN_COUNTERS * sizeof(unsigned int), ln->stream));
     GatherPolicy gp{ctx->d_table, ln->d_digits_t, ln->d_buf_a, fd, ctx->D};
     stage_begin(ctx, KZG_B200_STAGE_MSM_GATHER);
-    RC(launch_batch_add(ctx, gp, R * rows));
+    if (ctx->dynamic) RC(launch_batch_add_dyn(ctx, gp, R * rows, slot++));
+    else RC(launch_batch_add(ctx, gp, R * rows));
     stage_end(ctx, 1);
     g1_affine_t *in = ln->d_buf_a, *o = ln->d_buf_b;
     stage_begin(ctx, KZG_B200_STAGE_MSM_TREE);
@@ -325,7 +363,8 @@ static int run_msm(kzg_b200_ctx *ctx, size_t count, const g1_affine_t **out) {
     while (rows > 1) {
         rows /= 2;
         PairPolicy tp{in, o, fd};
-        RC(launch_batch_add(ctx, tp, R * rows));
+        if (ctx->dynamic) RC(launch_batch_add_dyn(ctx, tp, R * rows, slot++));
+        else RC(launch_batch_add(ctx, tp, R * rows, ctx->tree_blocks));
         std::swap(in, o);
         levels++;
     }
@@ -344,9 +383,9 @@ static size_t per_blob_workspace(const kzg_b200_ctx *ctx) {
 }
 static void free_workspace(kzg_b200_ctx *ctx) {
     for (auto &ln : ctx->lanes) {
-        cudaFree(ln.d_digits); cudaFree(ln.d_digits_t); cudaFree(ln.d_buf_a); cudaFree(ln.d_buf_b); cudaFree(ln.d_poly); cudaFree(ln.d_inv);
+        cudaFree(ln.d_digits); cudaFree(ln.d_digits_t); cudaFree(ln.d_counters); cudaFree(ln.d_buf_a); cudaFree(ln.d_buf_b); cudaFree(ln.d_poly); cudaFree(ln.d_inv);
         cudaFree(ln.d_z); cudaFree(ln.d_zy); cudaFree(ln.d_pts); cudaFree(ln.d_scratch);
-        ln.d_digits = ln.d_digits_t = nullptr; ln.d_buf_a = ln.d_buf_b = nullptr; ln.d_poly = ln.d_inv = ln.d_z = nullptr;
+        ln.d_digits = ln.d_digits_t = nullptr; ln.d_counters = nullptr; ln.d_buf_a = ln.d_buf_b = nullptr; ln.d_poly = ln.d_inv = ln.d_z = nullptr;
         ln.d_zy = nullptr; ln.d_pts = nullptr; ln.d_scratch = nullptr; ln.scratch_elems = 0;
     }
     cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_aux); cudaFree(ctx->d_stage_out); cudaFree(ctx->d_status);
@@ -361,6 +400,7 @@ static int alloc_workspace(kzg_b200_ctx *ctx, size_t chunk) {
         kzg_b200_ctx::Lane &ln = ctx->lanes[l];
         CU(cudaMalloc(&ln.d_digits, chunk * wn * sizeof(int32_t)));
         CU(cudaMalloc(&ln.d_digits_t, chunk * wn * sizeof(int32_t)));
+        CU(cudaMalloc(&ln.d_counters, KZG_DYN_COUNTERS * sizeof(unsigned int)));
         CU(cudaMalloc(&ln.d_buf_a, chunk * (wn / 2) * sizeof(g1_affine_t)));
         CU(cudaMalloc(&ln.d_buf_b, chunk * (wn / 4 + 1) * sizeof(g1_affine_t)));
         CU(cudaMalloc(&ln.d_poly, chunk * (size_t)ctx->n * sizeof(fr_t)));
@@ -457,6 +497,9 @@ extern "C" int kzg_b200_ctx_create(const uint8_t *g1_lagrange, size_t n1, const 
     ctx->max_k = env_int("KZG_B200_BATCH_K", 4096);
     ctx->add_blocks = env_int("KZG_B200_ADD_BLOCKS", 3) >= 4 ? 4 : 3;
     ctx->grid_mult = std::max(1, env_int("KZG_B200_GRID_MULT", 1));
+    ctx->dynamic = env_int("KZG_B200_DYNAMIC", 0) != 0;
+    ctx->tree_blocks = std::min(std::max(0, env_int("KZG_B200_TREE_BLOCKS", 0)), 4);
+    ctx->dyn_min_batch = std::max(1, env_int("KZG_B200_DYN_MIN_BATCH", 32));
     ctx->grid_blocks = std::max(1, env_int("KZG_B200_GRID_BLOCKS", ctx->add_blocks));
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KZG_B200_CUDA_ERROR; }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { kzg_b200_ctx_destroy(ctx); return KZG_B200_CUDA_ERROR; }
@@ -746,6 +789,12 @@ extern "C" int kzg_b200_measure_peaks(kzg_b200_ctx *ctx, double *imad_per_s, dou
 }
 
 // debugging aid (not declared in the public header): raw table entries, affine Montgomery limbs
+#ifdef KZG_TRACE
+extern "C" int kzg_b200_debug_set_trace(void *d_buf) {
+    unsigned long long *p = (unsigned long long *)d_buf;
+    return cudaMemcpyToSymbol(kzg::g_kzg_trace, &p, sizeof(p)) == cudaSuccess ? 0 : KZG_B200_CUDA_ERROR;
+}
+#endif
 extern "C" int kzg_b200_debug_table(kzg_b200_ctx *ctx, uint64_t first, uint64_t count, void *out) {
     if (!ctx) return KZG_B200_BAD_ARGS;
     std::lock_guard<std::mutex> lock(ctx->mu);

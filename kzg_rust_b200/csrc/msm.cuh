@@ -309,13 +309,180 @@ KZG_HD void batch_add_thread(const Policy &pol, uint64_t total, fp_t *scratch, i
     }
 }
 #if defined(__CUDACC__)
+#ifdef KZG_TRACE
+// experiment only (tools/trace_blocks.py): per-block start / end time and SM id of the last launch
+__device__ unsigned long long *g_kzg_trace = nullptr;
+KZG_D unsigned long long kzg_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+KZG_D unsigned kzg_smid() { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
+#endif
+// ------------------------------------------------------------------ the hot kernel, work-pulling form
+// batch_add_kernel gives every thread the same number of additions.  On the B200 that wastes a
+// fifth of the multiplier: the warp scheduler of an SM sub-partition serves its resident warps by
+// PRIORITY, not round-robin, so of the three blocks of an SM two run at full speed and finish at
+// 0.70 of the launch (gather level: 0.85) while the third starves and then runs alone -- one warp per
+// scheduler cannot keep the multiplier busy (measured with %globaltimer per warp, tools/trace_blocks.py).
+// Here the additions are cut into tiles of 32 (one per lane) and every WARP pulls tiles from a global
+// counter: whichever warps the scheduler favours simply take more tiles, and all warps finish together.
+//   * A warp works in batches: it pulls up to m tiles (pass 1: running product of the denominators,
+//     prefix products to its private scratch), inverts once for the whole warp (shuffle scans + one
+//     inversion, no block barrier anywhere), and unwinds the same tiles in reverse (pass 2).
+//   * m shrinks with the work that is left (guided self-scheduling), so the launch starts with long
+//     batches (few inversions) and ends with short ones (small imbalance at the end).
+//   * Tiles are handed out in index order, so at any moment all warps of the GPU work inside a window of
+//     a few thousand tiles: the locality of the point-major layout survives the dynamic order.
+KZG_D void warp_inverse(fp_t &inv, const fp_t &acc) {
+#if defined(__CUDA_ARCH__)
+    const int lane = threadIdx.x & 31;
+    fp_t pre = acc, suf = acc;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        fp_t t = shfl_up_fp(pre, d), u = shfl_down_fp(suf, d);
+        if (lane >= d) fe_mul(pre, pre, t);
+        if (lane + d < 32) fe_mul(suf, suf, u);
+    }
+    fp_t total;
+#pragma unroll
+    for (int i = 0; i < 12; i++) total.l[i] = __shfl_sync(0xffffffffu, pre.l[i], 31);
+    fp_t r;
+    fp_inv(r, total);  // the same value in every lane: no divergence
+    fp_t pe = shfl_up_fp(pre, 1), se = shfl_down_fp(suf, 1);
+    if (lane > 0) fe_mul(r, r, pe);
+    if (lane < 31) fe_mul(r, r, se);
+    inv = r;
+#endif
+}
+
+struct DynSchedule {
+    unsigned int *counter;  // next tile to hand out (zero before the launch)
+    uint32_t *tile_ids;     // [warps][cap]: the tiles of the current batch of each warp
+    fp_t *scratch;          // [warps][cap][32] prefix products
+    uint32_t ntiles;        // ceil(total / 32)
+    uint32_t cap;           // longest batch
+    uint32_t m_min;         // shortest batch (1 for small launches)
+};
+
+template <class Policy, int MINB>
+__global__ void __launch_bounds__(KZG_ADD_THREADS, MINB)
+batch_add_dyn_kernel(Policy pol, uint64_t total, DynSchedule ds) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    fp_t *scratch = ds.scratch + (size_t)warp * ds.cap * 32 + lane;
+    uint32_t *ids = ds.tile_ids + (size_t)warp * ds.cap;
+    const uint32_t NONE = 0xffffffffu;
+#ifdef KZG_TRACE
+    unsigned long long t0 = kzg_globaltimer();
+#endif
+    auto pull = [&]() -> uint32_t {  // lane 0 takes the next tile; every lane gets its index (NONE when exhausted)
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(ds.counter, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        return t < ds.ntiles ? t : NONE;
+    };
+    for (;;) {
+        // batch length from the work that is left
+        uint32_t seen = 0;
+        if (lane == 0) seen = *(volatile unsigned int *)ds.counter;
+        seen = __shfl_sync(0xffffffffu, seen, 0);
+        if (seen >= ds.ntiles) break;
+        uint32_t m = (ds.ntiles - seen) / (2 * nwarps);
+        m = m < ds.m_min ? ds.m_min : (m > ds.cap ? ds.cap : m);
+        // pass 1
+        fp_t acc = fe_one<FpParams>();
+        fp_t nx1, nx2;
+        uint32_t cnt = 0;
+        uint32_t tile = pull(), tile_n = NONE;
+        if (tile == NONE) break;
+        {
+            uint64_t g = (uint64_t)tile * 32 + lane;
+            if (g < total) { load_x(pol, g, 0, nx1); load_x(pol, g, 1, nx2); }
+        }
+        if (m > 1) tile_n = pull();
+#pragma unroll 1
+        for (uint32_t j = 0; j < m && tile != NONE; j++) {
+            const uint64_t g = (uint64_t)tile * 32 + lane;
+            fp_t x1 = nx1, x2 = nx2;
+            if (lane == 0) ids[j] = tile;
+            // operands of the next tile, and the index of the one after it, are requested before the multiplication
+            uint32_t tile_nn = NONE;
+            if (tile_n != NONE) {
+                uint64_t gn = (uint64_t)tile_n * 32 + lane;
+                if (gn < total) { load_x(pol, gn, 0, nx1); load_x(pol, gn, 1, nx2); }
+                if (j + 2 < m) tile_nn = pull();
+            }
+            if (g < total) {
+                fp_t den;
+                add_denominator(den, x1, x2, [&](fp_t &y) { load_y(pol, g, 0, y); }, [&](fp_t &y) { load_y(pol, g, 1, y); });
+                st_fp(scratch + (size_t)j * 32, acc);
+                fe_mul(acc, acc, den);
+            }
+            cnt++;
+            tile = tile_n;
+            tile_n = tile_nn;
+        }
+        __syncwarp();
+        fp_t inv;
+        warp_inverse(inv, acc);
+        // pass 2: unwind the same tiles in reverse
+        fp_t npre;
+        uint32_t t_cur = ids[cnt - 1];
+        {
+            uint64_t g = (uint64_t)t_cur * 32 + lane;
+            if (g < total) { load_x(pol, g, 0, nx1); load_x(pol, g, 1, nx2); ld_fp(npre, scratch + (size_t)(cnt - 1) * 32); }
+        }
+#pragma unroll 1
+        for (int j = (int)cnt - 1; j >= 0; j--) {
+            const uint64_t g = (uint64_t)t_cur * 32 + lane;
+            g1_affine_t p1, p2, r;
+            p1.x = nx1;
+            p2.x = nx2;
+            fp_t pre = npre;
+            const bool live = g < total;
+            if (live) { load_y(pol, g, 0, p1.y); load_y(pol, g, 1, p2.y); }
+            if (j > 0) {
+                t_cur = ids[j - 1];
+                uint64_t gp = (uint64_t)t_cur * 32 + lane;
+                if (gp < total) { load_x(pol, gp, 0, nx1); load_x(pol, gp, 1, nx2); ld_fp(npre, scratch + (size_t)(j - 1) * 32); }
+            }
+            if (live) {
+                fp_t den;
+                int kind = add_denominator(den, p1.x, p2.x, [&](fp_t &y) { y = p1.y; }, [&](fp_t &y) { y = p2.y; });
+                fp_t inv_j;
+                fe_mul(inv_j, inv, pre);
+                fe_mul(inv, inv, den);
+                add_finish(r, kind, p1, p2, inv_j);
+                g1_affine_t *o = pol.dst(g);
+                st_fp(&o->x, r.x);
+                st_fp(&o->y, r.y);
+            }
+        }
+        __syncwarp();
+    }
+#ifdef KZG_TRACE
+    if (g_kzg_trace && g_kzg_trace[0] == total && lane == 0) {
+        unsigned long long *r = g_kzg_trace + 4ull * (1 + warp);
+        r[0] = t0; r[1] = kzg_globaltimer(); r[2] = kzg_smid(); r[3] = total;
+    }
+#endif
+#endif
+}
+
 // MINB = resident blocks per SM the register allocation is tuned for (3: 168 registers, no
 // spills; 4: 128 registers, a few spilled words)
 template <class Policy, int MINB>
 __global__ void __launch_bounds__(KZG_ADD_THREADS, MINB)
 batch_add_kernel(Policy pol, uint64_t total, fp_t *__restrict__ scratch, int k) {
+#ifdef KZG_TRACE
+    unsigned long long t0 = kzg_globaltimer();
+#endif
     batch_add_thread(pol, total, scratch, k, (uint64_t)gridDim.x * blockDim.x,
                      (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+#ifdef KZG_TRACE
+    if (g_kzg_trace && g_kzg_trace[0] == total && (threadIdx.x & 31) == 0) {  // slot 0 = the launch to record
+        unsigned long long *r = g_kzg_trace + 4ull * (1 + blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32);
+        r[0] = t0; r[1] = kzg_globaltimer(); r[2] = kzg_smid(); r[3] = total;
+    }
+#endif
 }
 #endif
 

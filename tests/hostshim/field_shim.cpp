@@ -1,6 +1,7 @@
 // Host-side shim exposing the product's field templates (host code path of
 // kzg_rust_b200/csrc/bigint.cuh) to ctypes, so tests can compare them with Python ints.
 #include "../../kzg_rust_b200/csrc/fields.cuh"
+#include "../../kzg_rust_b200/csrc/fp_hybrid.cuh"
 using namespace kzg;
 extern "C" {
 void shim_fp_mul(const uint32_t *a, const uint32_t *b, uint32_t *r) { fp_t x, y, z; memcpy(x.l, a, 48); memcpy(y.l, b, 48); fe_mul(z, x, y); memcpy(r, z.l, 48); }
@@ -23,5 +24,34 @@ void shim_fp_mul_many(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t 
 }
 void shim_fr_mul_many(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t count) {
     for (size_t i = 0; i < count; i++) shim_fr_mul(a + 8 * i, b + 8 * i, r + 8 * i);
+}
+}
+// the two-pipe (FP64 product + IMAD reduction) multiplication of fp_hybrid.cuh, host code path
+extern "C" {
+void shim_fp_mul_hybrid_many(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t count) {
+    for (size_t i = 0; i < count; i++) {
+        fp_t x, y, z;
+        memcpy(x.l, a + 12 * i, 48); memcpy(y.l, b + 12 * i, 48);
+        fp_mul_hybrid(z, x, y);
+        memcpy(r + 12 * i, z.l, 48);
+    }
+}
+void shim_fp_sqr_hybrid_many(const uint32_t *a, uint32_t *r, size_t count) {
+    for (size_t i = 0; i < count; i++) {
+        fp_t x, z;
+        memcpy(x.l, a + 12 * i, 48);
+        fp_sqr_hybrid(z, x);
+        memcpy(r + 12 * i, z.l, 48);
+    }
+}
+void shim_fp_product_many(const uint32_t *a, const uint32_t *b, uint32_t *t, size_t count, int sqr) {
+    for (size_t i = 0; i < count; i++) {
+        fp_t x, y;
+        memcpy(x.l, a + 12 * i, 48); memcpy(y.l, b + 12 * i, 48);
+        if (sqr) hy_product<true>(t + 24 * i, x, x); else hy_product<false>(t + 24 * i, x, y);
+    }
+}
+void shim_fp_redc_many(const uint32_t *t, uint32_t *r, size_t count) {
+    for (size_t i = 0; i < count; i++) { fp_t z; fe_redc(z, t + 24 * i); memcpy(r + 12 * i, z.l, 48); }
 }
 }

@@ -191,3 +191,53 @@ def test_host_types_mirror_reference_length_checks():
     with pytest.raises(k.BadArgs):
         k.Kzg.verify_blob_kzg_proof_batch([k.Blob(bytes(131072))], [], [], None)
     assert k.Kzg.verify_blob_kzg_proof_batch([], [], [], None) is True
+
+
+def _pack(vals, n):
+    a = np.zeros((len(vals), n), dtype=np.uint32)
+    for r, v in enumerate(vals):
+        for i in range(n):
+            a[r, i] = (v >> (32 * i)) & 0xffffffff
+    return a
+
+
+def _unpack(a):
+    return [sum(int(x) << (32 * i) for i, x in enumerate(row)) for row in a]
+
+
+def test_two_pipe_fp_multiplication_vs_python(field):
+    """fp_hybrid.cuh (FP64-pipe product in 48-bit limbs + IMAD-pipe Montgomery reduction), host code
+    path with fma() under FE_TOWARDZERO: the 768-bit product, the reduction on its own, and the
+    product / square must equal Python integers -- and therefore fe_mul -- on edge and random values."""
+    rng = np.random.default_rng(7)
+    edge = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, 2 ** 380, 2 ** 381 - 1, 2 ** 48 - 1, 2 ** 48, (2 ** 48 - 1) * sum(2 ** (48 * k) for k in range(8)) % P,
+            sum((2 ** 48 - 1) << (96 * k) for k in range(4)) % P, 0xffffffff, 2 ** 336 - 1, 2 ** 336]
+    rand = [int.from_bytes(rng.bytes(48), "big") % P for _ in range(400)]
+    av = edge + rand + [e for e in edge for _ in edge]
+    bv = edge + rand[::-1] + [e for _ in edge for e in edge]
+    n = len(av)
+    a, b = _pack(av, 12), _pack(bv, 12)
+    ptr = lambda x: x.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+    Rinv = pow(pow(2, 384, P), -1, P)
+    # exact products
+    t = np.zeros((n, 24), dtype=np.uint32)
+    field.shim_fp_product_many(ptr(a), ptr(b), ptr(t), ctypes.c_size_t(n), 0)
+    assert _unpack(t) == [x * y for x, y in zip(av, bv)]
+    field.shim_fp_product_many(ptr(a), ptr(a), ptr(t), ctypes.c_size_t(n), 1)
+    assert _unpack(t) == [x * x for x in av]
+    # the reduction alone, over its whole domain T < p * 2^384
+    tv = [x * y for x, y in zip(av, bv)] + [P * 2 ** 384 - 1, (P - 1) * 2 ** 384, 2 ** 384 - 1, 2 ** 384, 0] + \
+         [int.from_bytes(rng.bytes(96), "big") % (P << 384) for _ in range(300)]
+    tt = _pack(tv, 24)
+    r = np.zeros((len(tv), 12), dtype=np.uint32)
+    field.shim_fp_redc_many(ptr(tt), ptr(r), ctypes.c_size_t(len(tv)))
+    assert _unpack(r) == [v * Rinv % P for v in tv]
+    # product and square against the integer-pipe fe_mul
+    r1 = np.zeros((n, 12), dtype=np.uint32)
+    r2 = np.zeros((n, 12), dtype=np.uint32)
+    field.shim_fp_mul_hybrid_many(ptr(a), ptr(b), ptr(r1), ctypes.c_size_t(n))
+    field.shim_fp_mul_many(ptr(a), ptr(b), ptr(r2), ctypes.c_size_t(n))
+    assert np.array_equal(r1, r2)
+    assert _unpack(r1) == [x * y * Rinv % P for x, y in zip(av, bv)]
+    field.shim_fp_sqr_hybrid_many(ptr(a), ptr(r1), ctypes.c_size_t(n))
+    assert _unpack(r1) == [x * x * Rinv % P for x in av]
