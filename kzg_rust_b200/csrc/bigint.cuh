@@ -169,7 +169,8 @@ template <class P> KZG_HD void fe_dbl(Fe<P> &r, const Fe<P> &a) { fe_add(r, a, a
 // Bounds (mod < 2^(32N-2)): V < 2 mod before a step and < 2 mod 2^32 inside it, hence
 // O < 2^(32N) always -- no chain on O ever carries out; a chain on E may, and that carry
 // (weight 2^(32N)) is added to O's top limb.  Inputs < mod, output < mod.
-template <class P> KZG_HD void fe_mul(Fe<P> &r, const Fe<P> &a, const Fe<P> &b) {
+// REDUCE = false skips the final conditional subtraction ("lazy" form, see fe_mul_lazy below).
+template <class P, bool REDUCE> KZG_HD void fe_mul_core(Fe<P> &r, const Fe<P> &a, const Fe<P> &b) {
     constexpr int N = P::N;
     uint32_t mp[N];
 #pragma unroll
@@ -214,10 +215,40 @@ template <class P> KZG_HD void fe_mul(Fe<P> &r, const Fe<P> &a, const Fe<P> &b) 
 #pragma unroll
     for (int k = 1; k < N - 1; k++) t.l[k] = addc_cc(O[k], E[k + 1], cc);
     t.l[N - 1] = addc(O[N - 1], 0, cc);
-    fe_reduce_once(t, 0);
+    if (REDUCE) fe_reduce_once(t, 0);
     r = t;
 }
+template <class P> KZG_HD void fe_mul(Fe<P> &r, const Fe<P> &a, const Fe<P> &b) { fe_mul_core<P, true>(r, a, b); }
 template <class P> KZG_HD void fe_sqr(Fe<P> &r, const Fe<P> &a) { fe_mul(r, a, a); }
+
+// ------------------------------------------------------------------ lazy residues: values in [0, 2 mod)
+// Every instruction beside the multiplier costs issue slots, so the hot loop of
+// the MSM keeps its values only partly reduced.  With R = 2^(32N) > 4 mod (Fp: R / mod = 9.8) the
+// Montgomery product of a, b < 2 mod is (a b + M mod) / R < 4 mod^2 / R + mod < 2 mod without any final
+// subtraction; inside the loop V stays below 3 mod 2^32, so the accumulator bounds of fe_mul_core hold.
+// Subtraction adds 2 mod back on a borrow.  Values are made canonical where they leave the loop.
+template <class P> KZG_HD void fe_mul_lazy(Fe<P> &r, const Fe<P> &a, const Fe<P> &b) { fe_mul_core<P, false>(r, a, b); }
+template <class P> KZG_HD void fe_sub_lazy(Fe<P> &r, const Fe<P> &a, const Fe<P> &b) {
+    uint32_t cc = 0;
+    Fe<P> t;
+    t.l[0] = sub_cc(a.l[0], b.l[0], cc);
+#pragma unroll
+    for (int i = 1; i < P::N; i++) t.l[i] = subc_cc(a.l[i], b.l[i], cc);
+    uint32_t borrow = subc(0, 0, cc);  // 0 or 0xffffffff
+    uint32_t c2 = 0;
+    r.l[0] = add_cc(t.l[0], P::mod2(0) & borrow, c2);
+#pragma unroll
+    for (int i = 1; i < P::N; i++) r.l[i] = addc_cc(t.l[i], P::mod2(i) & borrow, c2);
+}
+// [0, 2 mod) -> [0, mod)
+template <class P> KZG_HD void fe_canonical(Fe<P> &a) { fe_reduce_once(a, 0); }
+// a == 0 (mod m) for a in [0, 2 mod): a is 0 or mod.  The low limb filters out all but 2^-31 of the values.
+template <class P> KZG_HD bool fe_is_zero_lazy(const Fe<P> &a) {
+    if (a.l[0] != 0 && a.l[0] != P::mod(0)) return false;
+    Fe<P> c = a;
+    fe_canonical(c);
+    return fe_is_zero(c);
+}
 
 template <class P> KZG_HD void fe_to_mont(Fe<P> &r, const Fe<P> &a) {
     Fe<P> r2;

@@ -109,14 +109,20 @@ KZG_HD void fr_digits_thread(const fr_t *evals, uint64_t e, int n, int c, int W,
 // Horner pass over the W window sums of one blob: sum_j 2^(c j) S_j, S_j affine (possibly
 // infinity) at sums[j*stride] (the MSM leaves them window-major: stride = blobs in the chunk).
 // (W-1)(c doublings + 1 mixed addition) in Jacobian coordinates.
+// The sums come out of the lazy levels of the MSM with coordinates in [0, 2p): made canonical here.
+KZG_HD g1_affine_t horner_load(const g1_affine_t *p) {
+    g1_affine_t s = *p;
+    if (!g1a_is_inf(s)) { fe_canonical(s.x); fe_canonical(s.y); }
+    return s;
+}
 KZG_HD void horner_thread(g1_affine_t &out, const g1_affine_t *sums, size_t stride, int c, int W) {
     g1_jac_t acc;
-    g1j_from_affine(acc, sums[(size_t)(W - 1) * stride]);
+    g1j_from_affine(acc, horner_load(sums + (size_t)(W - 1) * stride));
 #pragma unroll 1
     for (int j = W - 2; j >= 0; j--) {
 #pragma unroll 1
         for (int k = 0; k < c; k++) g1j_dbl(acc, acc);
-        g1_affine_t s = sums[(size_t)j * stride];
+        g1_affine_t s = horner_load(sums + (size_t)j * stride);
         if (!g1a_is_inf(s)) g1j_add_affine(acc, acc, s.x, s.y);
     }
     g1j_to_affine(out, acc);

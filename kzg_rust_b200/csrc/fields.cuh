@@ -12,6 +12,10 @@ struct FpParams {
     static constexpr int N = 12;
     static constexpr uint32_t n0 = FP_N0;
     KZG_HD static constexpr uint32_t mod(int i) { constexpr uint32_t v[N] = {FP_P_LIMBS}; return v[i]; }
+    KZG_HD static constexpr uint32_t mod2(int i) {  // 2 p (fits: p < 2^381)
+        constexpr uint32_t v[N] = {FP_P_LIMBS};
+        return (v[i] << 1) | (i ? v[i - 1] >> 31 : 0u);
+    }
     KZG_HD static constexpr uint32_t r1(int i) { constexpr uint32_t v[N] = {FP_R1_LIMBS}; return v[i]; }
     KZG_HD static constexpr uint32_t r2(int i) { constexpr uint32_t v[N] = {FP_R2_LIMBS}; return v[i]; }
 };
@@ -19,6 +23,10 @@ struct FrParams {
     static constexpr int N = 8;
     static constexpr uint32_t n0 = FR_N0;
     KZG_HD static constexpr uint32_t mod(int i) { constexpr uint32_t v[N] = {FR_R_LIMBS}; return v[i]; }
+    KZG_HD static constexpr uint32_t mod2(int i) {  // 2 r (fits: r < 2^255)
+        constexpr uint32_t v[N] = {FR_R_LIMBS};
+        return (v[i] << 1) | (i ? v[i - 1] >> 31 : 0u);
+    }
     KZG_HD static constexpr uint32_t r1(int i) { constexpr uint32_t v[N] = {FR_R1_LIMBS}; return v[i]; }
     KZG_HD static constexpr uint32_t r2(int i) { constexpr uint32_t v[N] = {FR_R2_LIMBS}; return v[i]; }
 };

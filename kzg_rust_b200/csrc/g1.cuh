@@ -30,42 +30,54 @@ KZG_HD void g1a_set_inf(g1_affine_t &p) {
 //   P1 == -P2         -> den = 1, R = infinity
 enum { ADD_GENERIC = 0, ADD_TAKE_P2 = 1, ADD_TAKE_P1 = 2, ADD_DOUBLE = 3, ADD_CANCEL = 4 };
 
+// LAZY = true: coordinates, denominators and inverses are residues in [0, 2p) and stay so (fe_mul_lazy /
+// fe_sub_lazy, bigint.cuh); only the rare equal-x cases make their operands canonical.
+template <bool LAZY> KZG_HD void fpx_mul(fp_t &r, const fp_t &a, const fp_t &b) {
+    if (LAZY) fe_mul_lazy(r, a, b); else fe_mul(r, a, b);
+}
+template <bool LAZY> KZG_HD void fpx_sub(fp_t &r, const fp_t &a, const fp_t &b) {
+    if (LAZY) fe_sub_lazy(r, a, b); else fe_sub(r, a, b);
+}
 // y1/y2 are only read when x1 == x2 (the caller passes loaders so the common case does
 // not touch them in pass 1).
-template <class LoadY1, class LoadY2>
+template <bool LAZY, class LoadY1, class LoadY2>
 KZG_HD int add_denominator(fp_t &den, const fp_t &x1, const fp_t &x2, LoadY1 load_y1, LoadY2 load_y2) {
     if (fp_is_inf_marker(x1)) { den = fe_one<FpParams>(); return ADD_TAKE_P2; }
     if (fp_is_inf_marker(x2)) { den = fe_one<FpParams>(); return ADD_TAKE_P1; }
-    fe_sub(den, x2, x1);
-    if (!fe_is_zero(den)) return ADD_GENERIC;
+    fpx_sub<LAZY>(den, x2, x1);
+    if (!(LAZY ? fe_is_zero_lazy(den) : fe_is_zero(den))) return ADD_GENERIC;
     fp_t y1, y2;
     load_y1(y1);
     load_y2(y2);
+    if (LAZY) { fe_canonical(y1); fe_canonical(y2); }
     if (fe_eq(y1, y2) && !fe_is_zero(y1)) { fe_dbl(den, y1); return ADD_DOUBLE; }
     den = fe_one<FpParams>();
     return ADD_CANCEL;
 }
 // inv = 1/den for this addition
+template <bool LAZY>
 KZG_HD void add_finish(g1_affine_t &r, int kind, const g1_affine_t &p1, const g1_affine_t &p2, const fp_t &inv) {
     if (kind == ADD_TAKE_P2) { r = p2; return; }
     if (kind == ADD_TAKE_P1) { r = p1; return; }
     if (kind == ADD_CANCEL) { g1a_set_inf(r); return; }
     fp_t num, lam, t;
     if (kind == ADD_DOUBLE) {
-        fe_sqr(t, p1.x);
+        fp_t x = p1.x;
+        if (LAZY) fe_canonical(x);
+        fe_sqr(t, x);
         fe_dbl(num, t);
         fe_add(num, num, t);
     } else {
-        fe_sub(num, p2.y, p1.y);
+        fpx_sub<LAZY>(num, p2.y, p1.y);
     }
-    fe_mul(lam, num, inv);
-    fe_sqr(t, lam);
-    fe_sub(t, t, p1.x);
-    fe_sub(t, t, p2.x);  // x3 (p2.x == p1.x when doubling)
+    fpx_mul<LAZY>(lam, num, inv);
+    fpx_mul<LAZY>(t, lam, lam);
+    fpx_sub<LAZY>(t, t, p1.x);
+    fpx_sub<LAZY>(t, t, p2.x);  // x3 (p2.x == p1.x mod p when doubling)
     fp_t u;
-    fe_sub(u, p1.x, t);
-    fe_mul(u, lam, u);
-    fe_sub(r.y, u, p1.y);
+    fpx_sub<LAZY>(u, p1.x, t);
+    fpx_mul<LAZY>(u, lam, u);
+    fpx_sub<LAZY>(r.y, u, p1.y);
     r.x = t;
 }
 

@@ -82,6 +82,7 @@ struct FastDiv {
 //
 // Level >= 1: out[q*R + r] = in[2q*R + r] + in[(2q+1)*R + r]
 struct PairPolicy {
+    static constexpr bool lazy = true;  // coordinates in [0, 2p) between the levels of the MSM
     const g1_affine_t *in;
     g1_affine_t *out;
     FastDiv R;
@@ -96,6 +97,7 @@ struct PairPolicy {
 // General form (odd group sizes; used by the small sums of batch verification):
 // out[b][t] = in[b][2t] + in[b][2t+1]
 struct TreePolicy {
+    static constexpr bool lazy = false;
     const g1_affine_t *in;
     g1_affine_t *out;
     uint32_t cnt_in, cnt_out;  // points per blob before / after this level
@@ -113,6 +115,7 @@ struct TreePolicy {
 //   digits[(i*W + j)*count + b]  (int32, |d| <= D), point-major like the levels above:
 //   out[p*R + r] = sign * table[2p][|d(2p, r)|] + sign * table[2p+1][|d(2p+1, r)|],  r = j*count + b
 struct GatherPolicy {
+    static constexpr bool lazy = true;  // canonical table entries in, [0, 2p) out
     const g1_affine_t *table;
     const int32_t *digits;
     g1_affine_t *out;
@@ -133,6 +136,7 @@ struct GatherPolicy {
 // Table construction, level L: for every point s (= i) and d in (2^L, 2^(L+1)]:
 //   table[s][d] = table[s][d >> 1] + table[s][(d + 1) >> 1]
 struct TableLevelPolicy {
+    static constexpr bool lazy = false;  // the table is canonical
     g1_affine_t *table;
     uint32_t D;
     uint32_t level;
@@ -266,9 +270,9 @@ KZG_HD void batch_add_thread(const Policy &pol, uint64_t total, fp_t *scratch, i
             fp_t x1 = nx1, x2 = nx2, den;
             uint64_t gn = g + T;
             if (j + 1 < k && gn < total) { load_x(pol, gn, 0, nx1); load_x(pol, gn, 1, nx2); }
-            add_denominator(den, x1, x2, [&](fp_t &y) { load_y(pol, g, 0, y); }, [&](fp_t &y) { load_y(pol, g, 1, y); });
+            add_denominator<Policy::lazy>(den, x1, x2, [&](fp_t &y) { load_y(pol, g, 0, y); }, [&](fp_t &y) { load_y(pol, g, 1, y); });
             st_fp(scratch + (uint64_t)j * T + tid, acc);
-            fe_mul(acc, acc, den);
+            fpx_mul<Policy::lazy>(acc, acc, den);
             cnt++;
         }
         // every lane of the warp takes part (idle lanes contribute acc = 1)
@@ -297,11 +301,11 @@ KZG_HD void batch_add_thread(const Policy &pol, uint64_t total, fp_t *scratch, i
                 ld_fp(npre, scratch + (uint64_t)(j - 1) * T + tid);
             }
             fp_t den;
-            int kind = add_denominator(den, p1.x, p2.x, [&](fp_t &y) { y = p1.y; }, [&](fp_t &y) { y = p2.y; });
+            int kind = add_denominator<Policy::lazy>(den, p1.x, p2.x, [&](fp_t &y) { y = p1.y; }, [&](fp_t &y) { y = p2.y; });
             fp_t inv_j;
-            fe_mul(inv_j, inv, pre);
-            fe_mul(inv, inv, den);
-            add_finish(r, kind, p1, p2, inv_j);
+            fpx_mul<Policy::lazy>(inv_j, inv, pre);
+            fpx_mul<Policy::lazy>(inv, inv, den);
+            add_finish<Policy::lazy>(r, kind, p1, p2, inv_j);
             g1_affine_t *o = pol.dst(g);
             st_fp(&o->x, r.x);
             st_fp(&o->y, r.y);
@@ -412,9 +416,9 @@ batch_add_dyn_kernel(Policy pol, uint64_t total, DynSchedule ds) {
             }
             if (g < total) {
                 fp_t den;
-                add_denominator(den, x1, x2, [&](fp_t &y) { load_y(pol, g, 0, y); }, [&](fp_t &y) { load_y(pol, g, 1, y); });
+                add_denominator<Policy::lazy>(den, x1, x2, [&](fp_t &y) { load_y(pol, g, 0, y); }, [&](fp_t &y) { load_y(pol, g, 1, y); });
                 st_fp(scratch + (size_t)j * 32, acc);
-                fe_mul(acc, acc, den);
+                fpx_mul<Policy::lazy>(acc, acc, den);
             }
             cnt++;
             tile = tile_n;
@@ -446,11 +450,11 @@ batch_add_dyn_kernel(Policy pol, uint64_t total, DynSchedule ds) {
             }
             if (live) {
                 fp_t den;
-                int kind = add_denominator(den, p1.x, p2.x, [&](fp_t &y) { y = p1.y; }, [&](fp_t &y) { y = p2.y; });
+                int kind = add_denominator<Policy::lazy>(den, p1.x, p2.x, [&](fp_t &y) { y = p1.y; }, [&](fp_t &y) { y = p2.y; });
                 fp_t inv_j;
-                fe_mul(inv_j, inv, pre);
-                fe_mul(inv, inv, den);
-                add_finish(r, kind, p1, p2, inv_j);
+                fpx_mul<Policy::lazy>(inv_j, inv, pre);
+                fpx_mul<Policy::lazy>(inv, inv, den);
+                add_finish<Policy::lazy>(r, kind, p1, p2, inv_j);
                 g1_affine_t *o = pol.dst(g);
                 st_fp(&o->x, r.x);
                 st_fp(&o->y, r.y);

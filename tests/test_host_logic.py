@@ -241,3 +241,31 @@ def test_two_pipe_fp_multiplication_vs_python(field):
     assert _unpack(r1) == [x * y * Rinv % P for x, y in zip(av, bv)]
     field.shim_fp_sqr_hybrid_many(ptr(a), ptr(r1), ctypes.c_size_t(n))
     assert _unpack(r1) == [x * x * Rinv % P for x in av]
+
+
+def test_lazy_residues_vs_python(field):
+    """fe_mul_lazy / fe_sub_lazy (values in [0, 2p), no final subtraction): results stay below 2p and are
+    congruent to the exact ones; zero test and canonicalisation agree with Python."""
+    rng = np.random.default_rng(11)
+    edge = [0, 1, P - 1, P, P + 1, 2 * P - 1, 2 * P - 2, (P - 1) // 2, 2 ** 381, 2 ** 382 - 1 if 2 ** 382 - 1 < 2 * P else 2 * P - 3]
+    rand = [int.from_bytes(rng.bytes(49), "big") % (2 * P) for _ in range(500)]
+    av = rand + [e for e in edge for _ in edge]
+    bv = rand[::-1] + [e for _ in edge for e in edge]
+    n = len(av)
+    a, b = _pack(av, 12), _pack(bv, 12)
+    ptr = lambda x: x.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+    Rinv = pow(pow(2, 384, P), -1, P)
+    r = np.zeros((n, 12), dtype=np.uint32)
+    field.shim_fp_mul_lazy_many(ptr(a), ptr(b), ptr(r), ctypes.c_size_t(n))
+    got = _unpack(r)
+    assert all(g < 2 * P for g in got)
+    assert [g % P for g in got] == [x * y * Rinv % P for x, y in zip(av, bv)]
+    field.shim_fp_sub_lazy_many(ptr(a), ptr(b), ptr(r), ctypes.c_size_t(n))
+    got = _unpack(r)
+    assert all(g < 2 * P for g in got)
+    assert [g % P for g in got] == [(x - y) % P for x, y in zip(av, bv)]
+    out = (ctypes.c_uint32 * 12)()
+    for v in edge + rand[:50]:
+        assert bool(field.shim_fp_is_zero_lazy(_limbs(v, 12))) == (v % P == 0)
+        field.shim_fp_canonical(_limbs(v, 12), out)
+        assert _val(out) == v % P
