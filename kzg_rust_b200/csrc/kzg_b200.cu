@@ -89,6 +89,8 @@ struct kzg_b200_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_h2d[KZG_SLOTS] = {nullptr, nullptr, nullptr}, ev_free[KZG_SLOTS] = {nullptr, nullptr, nullptr};
     host_g2_prepared *tau_prepared = nullptr;  // Miller-loop lines of [tau]G2
+    fr_t *d_z_all = nullptr;          // challenges of a whole device-resident proof call (grow-only)
+    size_t z_all_elems = 0;
     uint8_t *d_vb = nullptr;          // phase-B buffer of batch verification (grow-only)
     size_t vb_bytes = 0;
     cudaStream_t stream = nullptr;
@@ -589,6 +591,7 @@ extern "C" void kzg_b200_ctx_destroy(kzg_b200_ctx *ctx) {
     if (ctx->lanes[1].stream) cudaStreamSynchronize(ctx->lanes[1].stream);
     free_workspace(ctx);
     cudaFree(ctx->d_vb);
+    cudaFree(ctx->d_z_all);
     cudaFree(ctx->d_table);
     cudaFree(ctx->d_roots);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

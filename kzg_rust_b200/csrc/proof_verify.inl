@@ -17,16 +17,22 @@ static int decode_points(kzg_b200_ctx *ctx, const uint8_t *d_bytes, g1_affine_t 
 // One chunk on the device.  Exactly one of d_commitments (blob proof: z from the Fiat-Shamir
 // hash, reference src/kzg.rs:533-544) and d_zbytes (proof at a caller-supplied point,
 // src/kzg.rs:446-457) is non-null.  d_zy (optional) receives z || y.
+// d_z_ready (optional): challenges of this chunk already computed (device-resident calls hash all blobs of
+// the call in one launch: a 4096-blob chunk alone is 28 SHA-256 streams per SM, which is latency-bound).
 static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments, const uint8_t *d_zbytes,
-                       size_t count, uint8_t *d_proofs, uint8_t *d_zy, int32_t *d_status) {
+                       size_t count, uint8_t *d_proofs, uint8_t *d_zy, int32_t *d_status, const fr_t *d_z_ready = nullptr) {
     kzg_b200_ctx::Lane *ln = ctx->cur;
     cudaStream_t st = ln->stream;
     CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), st));
     if (d_commitments) {
         RC(decode_points(ctx, d_commitments, ln->d_pts, d_status, count, 1, count));
-        stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
-        k_challenge<<<blocks_for(count, 64), 64, 0, st>>>(d_blobs, d_commitments, (uint32_t)count, ctx->n, ln->d_z);
-        stage_end(ctx, 1);
+        if (d_z_ready) {
+            CU(cudaMemcpyAsync(ln->d_z, d_z_ready, count * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+        } else {
+            stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
+            k_challenge<<<blocks_for(count, 64), 64, 0, st>>>(d_blobs, d_commitments, (uint32_t)count, ctx->n, ln->d_z);
+            stage_end(ctx, 1);
+        }
     } else {
         k_load_scalars<<<blocks_for(count, 128), 128, 0, st>>>(d_zbytes, (uint32_t)count, ln->d_z, d_status);
     }
@@ -53,13 +59,31 @@ extern "C" int kzg_b200_compute_blob_kzg_proof_device(kzg_b200_ctx *ctx, const u
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     const size_t bpb = (size_t)ctx->n * 32;
+    // all Fiat-Shamir challenges of the call in one launch on the caller-visible stream, before the lanes fork
+    const fr_t *d_z_all = nullptr;
+    if (n > ctx->chunk) {
+        if (n > ctx->z_all_elems) {
+            if (ctx->d_z_all) CU(cudaFree(ctx->d_z_all));
+            ctx->d_z_all = nullptr;
+            ctx->z_all_elems = 0;
+            CU(cudaMalloc(&ctx->d_z_all, n * sizeof(fr_t)));
+            ctx->z_all_elems = n;
+        }
+        ctx->cur = &ctx->lanes[0];
+        stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
+        k_challenge<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(d_blobs, d_commitments, (uint32_t)n, ctx->n, ctx->d_z_all);
+        stage_end(ctx, 1);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        d_z_all = ctx->d_z_all;
+    }
     RC(lanes_begin(ctx));
     size_t i = 0;
     for (size_t off = 0; off < n; off += ctx->chunk, i++) {
         size_t cnt = std::min(ctx->chunk, n - off);
         lane_select(ctx, i);
         RC(proof_chunk(ctx, d_blobs + off * bpb, d_commitments + off * 48, nullptr, cnt, d_proofs_out + off * 48, nullptr,
-                       d_status + off));
+                       d_status + off, d_z_all ? d_z_all + off : nullptr));
     }
     return lanes_end(ctx);
 }

@@ -144,3 +144,40 @@ def test_minimal_preset_proofs_vs_oracle():
         for i in range(4):
             ep, ey = o.compute_kzg_proof(blobs[128 * i:128 * i + 128], zb)
             assert p[i].tobytes() == ep and y[i].tobytes() == ey, (z, i)
+
+
+def test_device_resident_calls_span_chunks_vs_oracle():
+    """The *_device entry points (caller-owned device buffers, asynchronous on the context's stream) over
+    more blobs than one workspace chunk: commitments and proofs byte-equal with the oracle.  The proof call
+    hashes the Fiat-Shamir challenges of the whole call in one launch before the chunks start."""
+    import torch
+    k = _kzg()
+    L = k.load_library()
+    os.environ["KZG_B200_CHUNK"] = "24"
+    try:
+        s = k.KzgSettings.load_trusted_setup(G.g1_bytes, G.g2_bytes, 0, 7)
+    finally:
+        del os.environ["KZG_B200_CHUNK"]
+    o = oracle_settings("mainnet")
+    n = 64
+    blobs = synthetic_blobs(n, seed=0xD3)
+    blobs[7, :] = 0
+    blobs[30] = blobs[29]
+    dev = torch.device("cuda", 0)
+    d_blobs = torch.from_numpy(blobs).to(dev)
+    d_cm = torch.zeros((n, 48), dtype=torch.uint8, device=dev)
+    d_pr = torch.zeros((n, 48), dtype=torch.uint8, device=dev)
+    d_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    assert L.kzg_b200_blob_to_kzg_commitment_device(s._h, d_blobs.data_ptr(), n, d_cm.data_ptr(), d_st.data_ptr()) == 0
+    L.kzg_b200_synchronize(s._h)
+    assert not bool(d_st.any().item())
+    exp_c, est = o.blob_to_kzg_commitment_many(blobs, nthreads=os.cpu_count() or 1)
+    assert not est.any() and np.array_equal(d_cm.cpu().numpy(), exp_c)
+    for _ in range(2):  # twice: the second call reuses the grow-only challenge buffer
+        assert L.kzg_b200_compute_blob_kzg_proof_device(s._h, d_blobs.data_ptr(), d_cm.data_ptr(), n, d_pr.data_ptr(), d_st.data_ptr()) == 0
+        L.kzg_b200_synchronize(s._h)
+        assert not bool(d_st.any().item())
+        exp_p, est = o.compute_blob_kzg_proof_many(blobs, exp_c, nthreads=os.cpu_count() or 1)
+        assert not est.any() and np.array_equal(d_pr.cpu().numpy(), exp_p)
+        d_pr.zero_()
+    s.close()
