@@ -315,7 +315,12 @@ def main():
     roofline = {
         "bound": "imad", "kernel": "batch_add_kernel (GatherPolicy + TreePolicy launches)",
         "achieved": achieved / 1e12, "peak": imad.value / 1e12, "unit": "TIMAD/s", "frac": achieved / imad.value if imad.value else None,
-        "traffic": None,
+        # DRAM bytes per average launch, from `ncu --set full` of one gather-level and one level-1 launch of a
+        # 4096-blob chunk at c = 19 (profiles/ncu_batch_add_r1c.md: 99.8 GB and 33.8 GB read + written);
+        # levels 2..11 halve each time, 12 launches per chunk.  The MSM streams the selected table rows and the
+        # intermediate levels through HBM by design (40 % of the HBM peak) to do 36 % fewer additions.
+        "traffic": (99.8e9 + 2 * 33.8e9) / 12 if s.window_bits == 19 else None,
+        "traffic_unit": "DRAM bytes per average batch_add launch (ncu, 4096-blob chunk)",
         "launches": msm_launches, "avg_launch_ms": msm_ms / max(1, msm_launches),
         "algorithmic_imad_per_blob": IMAD_PER_COMMIT,
         "peak_source": "mad.lo.u32 issue-rate micro-benchmark run in this process (kzg_b200_measure_peaks); "
