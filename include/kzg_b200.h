@@ -176,6 +176,13 @@ int kzg_b200_pairings_verify(const uint8_t a1[48], const uint8_t a2[96], const u
  * and of dependent full Fp Montgomery multiplications (mul/s).  */
 int kzg_b200_measure_peaks(kzg_b200_ctx *ctx, double *imad_per_s, double *imad_wide_per_s, double *fp_mul_per_s);
 
+/* Test aids (tests/test_gpu_field.py, tests/test_gpu_commit.py): device field arithmetic on arrays of raw
+ * limbs -- op 0: Fp mul, 1: Fp inverse, 2: Fr mul (8 words per element, all others 12), 3: Fp add, 4: Fp sub,
+ * 5 / 6: Fp mul / square with the product formed on the FP64 pipe (csrc/fp_hybrid.cuh), 7 / 8: Fp mul / sub
+ * on lazy residues in [0, 2p) (what the MSM levels use) -- and a read-back of precomputed table entries. */
+int kzg_b200_debug_field_op(kzg_b200_ctx *ctx, int op, const uint32_t *a, const uint32_t *b, uint32_t *out, uint64_t count);
+int kzg_b200_debug_table(kzg_b200_ctx *ctx, uint64_t first, uint64_t count, void *out);
+
 #ifdef __cplusplus
 }
 #endif

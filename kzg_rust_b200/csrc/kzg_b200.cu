@@ -18,6 +18,7 @@
 #include "frpath.cuh"
 #include "host_pairing.h"
 #include "msm.cuh"
+#include "fp_hybrid.cuh"
 
 using namespace kzg;
 
@@ -807,7 +808,8 @@ extern "C" int kzg_b200_debug_table(kzg_b200_ctx *ctx, uint64_t first, uint64_t 
 }
 
 // debugging / unit-test aid: device field operations on arrays (op 0: Fp mul, 1: Fp inverse (b ignored),
-// 2: Fr mul, 3: Fp add, 4: Fp sub).  Operands are raw limbs (12 or 8 words each).
+// 2: Fr mul, 3: Fp add, 4: Fp sub, 5: two-pipe Fp mul (fp_hybrid.cuh), 6: two-pipe Fp square (b ignored),
+// 7: lazy Fp mul, 8: lazy Fp sub -- operands and results in [0, 2p)).  Operands are raw limbs (12 or 8 words each).
 __global__ void k_debug_field_op(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, uint64_t count) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -823,6 +825,10 @@ __global__ void k_debug_field_op(int op, const uint32_t *a, const uint32_t *b, u
     if (op == 0) fe_mul(z, x, y);
     else if (op == 1) fp_inv(z, x);
     else if (op == 3) fe_add(z, x, y);
+    else if (op == 5) fp_mul_hybrid(z, x, y);
+    else if (op == 6) fp_sqr_hybrid(z, x);
+    else if (op == 7) fe_mul_lazy(z, x, y);
+    else if (op == 8) fe_sub_lazy(z, x, y);
     else fe_sub(z, x, y);
     for (int k = 0; k < 12; k++) out[12 * i + k] = z.l[k];
 }

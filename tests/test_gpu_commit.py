@@ -107,3 +107,27 @@ def test_large_batch_spans_chunks():
     for rep in range(16):
         assert np.array_equal(out[16 * rep:16 * rep + 16], exp)
     s.close()
+
+
+def test_work_pulling_kernel_vs_oracle():
+    """KZG_B200_DYNAMIC=1: the MSM levels run batch_add_dyn_kernel (warps pull 32-addition tiles from a
+    counter, per-warp inversion).  Same bytes as the oracle, special cases included, several chunks."""
+    k = _kzg()
+    os.environ["KZG_B200_DYNAMIC"] = "1"
+    os.environ["KZG_B200_CHUNK"] = "40"
+    try:
+        g = golden()
+        s = k.KzgSettings.load_trusted_setup(g.g1_bytes, g.g2_bytes, 0, 9)
+    finally:
+        del os.environ["KZG_B200_DYNAMIC"]
+        del os.environ["KZG_B200_CHUNK"]
+    blobs = synthetic_blobs(100, seed=0xD1)
+    blobs[3, :] = 0                      # every addition meets infinity
+    blobs[4] = 0
+    blobs[4, 31::32] = 1                 # the constant polynomial 1: equal digits everywhere
+    blobs[50] = blobs[49]
+    out, status = k.Kzg.blob_to_kzg_commitment_batch(blobs, s)
+    assert not status.any()
+    exp, est = oracle_settings("mainnet").blob_to_kzg_commitment_many(blobs, nthreads=os.cpu_count() or 1)
+    assert not est.any() and np.array_equal(out, exp)
+    s.close()
