@@ -311,6 +311,8 @@ def main():
     msm_launches = int(stage_ln[1] + stage_ln[2])
     blobs_timed = B  # the profiled step
     achieved = IMAD_PER_COMMIT * blobs_timed / (msm_ms * 1e-3) if msm_ms > 0 else 0.0
+    n_windows = {19: 14, 18: 15}.get(s.window_bits, -(-255 // s.window_bits))
+    executed_imad = n_windows * 4095 * 6 * 600.0
     wn = None
     roofline = {
         "bound": "imad", "kernel": "batch_add_kernel (GatherPolicy + TreePolicy launches)",
@@ -327,6 +329,10 @@ def main():
                        "MEASURED_PEAKS.json has no integer figure",
         "wide_mac_per_s": imadw.value, "fp_mul_per_s": fpmul.value,
         "whole_step_frac": IMAD_PER_COMMIT * value / world / imad.value if imad.value else None,
+        # against the work this design actually executes: W windows x (n - 1) additions x 6 products x 600 IMAD slots
+        "executed_imad_per_blob": executed_imad,
+        "executed_frac": executed_imad * blobs_timed / (msm_ms * 1e-3) / imad.value if imad.value and msm_ms > 0 else None,
+        "executed_whole_step_frac": executed_imad * value / world / imad.value if imad.value else None,
         "hbm": {"achieved_gbs": HBM_BYTES_PER_COMMIT * value / world / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                 "frac": HBM_BYTES_PER_COMMIT * value / world / 1e9 / peaks.get("hbm_gbs", 1.0), "peak_kind": peaks_kind},
         "stage_ms_per_step": {STAGES[i]: stage_ms[i] for i in range(8) if stage_ms[i] > 0},
