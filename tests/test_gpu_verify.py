@@ -1,6 +1,7 @@
 """-m gpu: verify_blob_kzg_proof / verify_blob_kzg_proof_batch through the C ABI against the
 reference's vectors, plus the two-phase (sharded) form used for multi-GPU verification."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -147,3 +148,50 @@ def test_pairing_check_matches_oracle():
         ok = ctypes.c_int(-1)
         assert L.kzg_b200_pairings_verify(a1, a2, b1, b2, ctypes.byref(ok)) == 0
         assert bool(ok.value) is ob.pairings_verify(a1, a2, b1, b2)
+
+
+def test_config5_size_16384_blobs_round_trip_properties():
+    """BASELINE.json configs[3..4] size on one GPU, checked through size-independent properties: 16,384
+    synthetic blobs are committed and proved on the device (default window width, several chunks, both
+    lanes), then (1) the whole batch verifies -- one pairing equation over all 16,384 (C_i, proof_i), which
+    holds only if every proof opens its commitment at its own challenge, (2) the same batch with two proofs
+    swapped is rejected, (3) repeated blobs give repeated commitments and proofs wherever they sit in the
+    batch, (4) a sample is byte-equal with the oracle."""
+    import ctypes
+    import torch
+    import kzg_rust_b200 as k
+    L = k.load_library()
+    s = k.KzgSettings.load_trusted_setup(G.g1_bytes, G.g2_bytes, 0, 0)
+    n = 16384
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0xC5)
+    d_blobs = torch.randint(0, 256, (n, 4096, 32), dtype=torch.uint8, device=dev, generator=gen)
+    d_blobs[:, :, 0] = 0
+    d_blobs[9000] = d_blobs[17]          # repeats across chunks and lanes
+    d_blobs[16383] = d_blobs[4096]
+    d_blobs[5000] = 0                    # the zero polynomial
+    d_cm = torch.zeros((n, 48), dtype=torch.uint8, device=dev)
+    d_pr = torch.zeros((n, 48), dtype=torch.uint8, device=dev)
+    d_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    assert L.kzg_b200_blob_to_kzg_commitment_device(s._h, d_blobs.data_ptr(), n, d_cm.data_ptr(), d_st.data_ptr()) == 0
+    assert L.kzg_b200_compute_blob_kzg_proof_device(s._h, d_blobs.data_ptr(), d_cm.data_ptr(), n, d_pr.data_ptr(), d_st.data_ptr()) == 0
+    L.kzg_b200_synchronize(s._h)
+    assert not bool(d_st.any().item())
+    cms, prs = d_cm.cpu().numpy(), d_pr.cpu().numpy()
+    assert np.array_equal(cms[9000], cms[17]) and np.array_equal(prs[9000], prs[17])
+    assert np.array_equal(cms[16383], cms[4096]) and np.array_equal(prs[16383], prs[4096])
+    assert cms[5000].tobytes() == b"\xc0" + bytes(47) and prs[5000].tobytes() == b"\xc0" + bytes(47)
+    blobs = torch.empty((n, 131072), dtype=torch.uint8, pin_memory=True).copy_(d_blobs.reshape(n, 131072)).numpy()
+    del d_blobs
+    assert k.Kzg.verify_blob_kzg_proof_batch_raw(blobs, cms, prs, n, s) is True
+    bad = prs.copy()
+    bad[[123, 15000]] = bad[[15000, 123]]
+    assert k.Kzg.verify_blob_kzg_proof_batch_raw(blobs, cms, bad, n, s) is False
+    idx = [0, 17, 4095, 4096, 5000, 8191, 12288, 16383]
+    o = oracle_settings("mainnet")
+    exp_c, est = o.blob_to_kzg_commitment_many(blobs[idx], nthreads=os.cpu_count() or 1)
+    assert not est.any() and np.array_equal(cms[idx], exp_c)
+    exp_p, est = o.compute_blob_kzg_proof_many(blobs[idx], exp_c, nthreads=os.cpu_count() or 1)
+    assert not est.any() and np.array_equal(prs[idx], exp_p)
+    s.close()
