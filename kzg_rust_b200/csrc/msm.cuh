@@ -210,6 +210,15 @@ KZG_HD void load_y_d(const Policy &pol, uint64_t g, int which, int d, fp_t &y) {
     if (neg) fe_neg(y, y);
 }
 
+// y as stored, with the sign still to be applied: the negation is the first consumer of the load, so it is
+// deferred until two products later (ncu: 11 % of the gather level's stall samples sat on it)
+template <class Policy>
+KZG_HD void load_y_raw_d(const Policy &pol, uint64_t g, int which, int d, fp_t &y, bool &neg) {
+    const g1_affine_t *p = pol.src_d(g, which, d, neg);
+    if (p == nullptr) { fe_set_zero(y); neg = false; return; }
+    ld_fp(y, &p->y);
+}
+
 // ------------------------------------------------------------------ the hot kernel
 // total additions, spread as g = base + j*T + tid (j < k) so neighbouring threads touch
 // neighbouring memory.  scratch holds T*k prefix products (48 B each).
@@ -334,8 +343,9 @@ KZG_HD void batch_add_thread(const Policy &pol, uint64_t total, fp_t *scratch, i
             p1.x = nx1;
             p2.x = nx2;
             fp_t pre = npre;
-            load_y_d(pol, g, 0, dc0, p1.y);
-            load_y_d(pol, g, 1, dc1, p2.y);
+            bool ng1, ng2;
+            load_y_raw_d(pol, g, 0, dc0, p1.y, ng1);
+            load_y_raw_d(pol, g, 1, dc1, p2.y, ng2);
             if (j > 0) {
                 load_x_d(pol, g - T, 0, dn0, nx1);
                 load_x_d(pol, g - T, 1, dn1, nx2);
@@ -345,10 +355,13 @@ KZG_HD void batch_add_thread(const Policy &pol, uint64_t total, fp_t *scratch, i
                 if (j > 1) { dn0 = pol.digit(g - 2 * T, 0); dn1 = pol.digit(g - 2 * T, 1); }
             }
             fp_t den;
-            int kind = add_denominator<Policy::lazy>(den, p1.x, p2.x, [&](fp_t &y) { y = p1.y; }, [&](fp_t &y) { y = p2.y; });
+            int kind = add_denominator<Policy::lazy>(
+                den, p1.x, p2.x, [&](fp_t &y) { y = p1.y; if (ng1) fe_neg(y, y); }, [&](fp_t &y) { y = p2.y; if (ng2) fe_neg(y, y); });
             fp_t inv_j;
             fpx_mul<Policy::lazy>(inv_j, inv, pre);
             fpx_mul<Policy::lazy>(inv, inv, den);
+            if (ng1) fe_neg(p1.y, p1.y);
+            if (ng2) fe_neg(p2.y, p2.y);
             add_finish<Policy::lazy>(r, kind, p1, p2, inv_j);
             g1_affine_t *o = pol.dst(g);
             st_fp(&o->x, r.x);
