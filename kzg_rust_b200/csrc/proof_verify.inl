@@ -23,17 +23,19 @@ static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t 
                        size_t count, uint8_t *d_proofs, uint8_t *d_zy, int32_t *d_status, const fr_t *d_z_ready = nullptr) {
     kzg_b200_ctx::Lane *ln = ctx->cur;
     cudaStream_t st = ln->stream;
-    CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), st));
-    if (d_commitments) {
+    if (d_z_ready) {
+        // the caller validated the commitments (status already holds the verdicts) and hashed the challenges
+        CU(cudaMemcpyAsync(ln->d_z, d_z_ready, count * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+    } else if (d_commitments) {
+        CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), st));
         RC(decode_points(ctx, d_commitments, ln->d_pts, d_status, count, 1, count));
-        if (d_z_ready) {
-            CU(cudaMemcpyAsync(ln->d_z, d_z_ready, count * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
-        } else {
+        {
             stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
             k_challenge<<<blocks_for(count, 64), 64, 0, st>>>(d_blobs, d_commitments, (uint32_t)count, ctx->n, ln->d_z);
             stage_end(ctx, 1);
         }
     } else {
+        CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), st));
         k_load_scalars<<<blocks_for(count, 128), 128, 0, st>>>(d_zbytes, (uint32_t)count, ln->d_z, d_status);
     }
     ctx->launches++;
@@ -59,17 +61,20 @@ extern "C" int kzg_b200_compute_blob_kzg_proof_device(kzg_b200_ctx *ctx, const u
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     const size_t bpb = (size_t)ctx->n * 32;
-    // all Fiat-Shamir challenges of the call in one launch on the caller-visible stream, before the lanes fork
+    // all commitment validations and Fiat-Shamir challenges of the call in one launch each on the
+    // caller-visible stream, before the lanes fork (per 4096-blob chunk both are latency-bound)
     const fr_t *d_z_all = nullptr;
     if (n > ctx->chunk) {
         if (n > ctx->z_all_elems) {
             if (ctx->d_z_all) CU(cudaFree(ctx->d_z_all));
             ctx->d_z_all = nullptr;
             ctx->z_all_elems = 0;
-            CU(cudaMalloc(&ctx->d_z_all, n * sizeof(fr_t)));
+            CU(cudaMalloc(&ctx->d_z_all, n * (sizeof(fr_t) + sizeof(g1_affine_t))));
             ctx->z_all_elems = n;
         }
         ctx->cur = &ctx->lanes[0];
+        CU(cudaMemsetAsync(d_status, 0, n * sizeof(int32_t), ctx->stream));
+        RC(decode_points(ctx, d_commitments, reinterpret_cast<g1_affine_t *>(ctx->d_z_all + n), d_status, n, 1, n));
         stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
         k_challenge<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(d_blobs, d_commitments, (uint32_t)n, ctx->n, ctx->d_z_all);
         stage_end(ctx, 1);

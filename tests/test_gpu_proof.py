@@ -180,4 +180,15 @@ def test_device_resident_calls_span_chunks_vs_oracle():
         exp_p, est = o.compute_blob_kzg_proof_many(blobs, exp_c, nthreads=os.cpu_count() or 1)
         assert not est.any() and np.array_equal(d_pr.cpu().numpy(), exp_p)
         d_pr.zero_()
+    # a commitment that is not a curve point and one outside the subgroup: only those blobs are refused
+    # (the whole call's commitments are validated in one launch before the chunks start)
+    bad = d_cm.clone()
+    bad[5, 47] ^= 1
+    bad[40, 1] ^= 0x55
+    assert L.kzg_b200_compute_blob_kzg_proof_device(s._h, d_blobs.data_ptr(), bad.data_ptr(), n, d_pr.data_ptr(), d_st.data_ptr()) == 0
+    L.kzg_b200_synchronize(s._h)
+    st = d_st.cpu().numpy()
+    from oracle.binding import validate_kzg_g1
+    expect_bad = [i for i in (5, 40) if not validate_kzg_g1(bad[i].cpu().numpy().tobytes())]
+    assert sorted(np.nonzero(st)[0].tolist()) == sorted(expect_bad) and len(expect_bad) >= 1
     s.close()
