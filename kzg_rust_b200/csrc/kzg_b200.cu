@@ -88,6 +88,8 @@ struct kzg_b200_ctx {
     uint8_t *d_stage_out = nullptr;   // slots x chunk x 96 B
     int32_t *d_status = nullptr;      // slots x chunk
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t side_stream = nullptr;   // small verification calls: point validation beside the challenge hash
+    cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr;
     cudaEvent_t ev_h2d[KZG_SLOTS] = {nullptr, nullptr, nullptr}, ev_free[KZG_SLOTS] = {nullptr, nullptr, nullptr};
     host_g2_prepared *tau_prepared = nullptr;  // Miller-loop lines of [tau]G2
     fr_t *d_z_all = nullptr;          // challenges of a whole device-resident proof call (grow-only)
@@ -506,6 +508,9 @@ extern "C" int kzg_b200_ctx_create(const uint8_t *g1_lagrange, size_t n1, const 
     ctx->grid_blocks = std::max(1, env_int("KZG_B200_GRID_BLOCKS", ctx->add_blocks));
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KZG_B200_CUDA_ERROR; }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { kzg_b200_ctx_destroy(ctx); return KZG_B200_CUDA_ERROR; }
+    if (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_side_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_side_join, cudaEventDisableTiming) != cudaSuccess) { kzg_b200_ctx_destroy(ctx); return KZG_B200_CUDA_ERROR; }
     ctx->nlanes = env_int("KZG_B200_LANES", 2) >= 2 ? 2 : 1;
     ctx->lanes[0].stream = ctx->stream;
     if (cudaStreamCreateWithFlags(&ctx->lanes[1].stream, cudaStreamNonBlocking) != cudaSuccess) { kzg_b200_ctx_destroy(ctx); return KZG_B200_CUDA_ERROR; }
@@ -597,6 +602,9 @@ extern "C" void kzg_b200_ctx_destroy(kzg_b200_ctx *ctx) {
     cudaFree(ctx->d_roots);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->ev_side_fork) cudaEventDestroy(ctx->ev_side_fork);
+    if (ctx->ev_side_join) cudaEventDestroy(ctx->ev_side_join);
     if (ctx->lanes[1].stream) cudaStreamDestroy(ctx->lanes[1].stream);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     for (int i = 0; i < 2; i++)

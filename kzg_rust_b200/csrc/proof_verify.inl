@@ -12,6 +12,20 @@ static int decode_points(kzg_b200_ctx *ctx, const uint8_t *d_bytes, g1_affine_t 
     CU(cudaGetLastError());
     return KZG_B200_OK;
 }
+// The same on the context's side stream, forked from and joined to the current lane's stream by the caller:
+// small verification calls are chains of latency-bound kernels, and decompression + subgroup checks (2.2 ms)
+// do not depend on the challenge hash (3.1 ms) that runs meanwhile.
+static int decode_points_side(kzg_b200_ctx *ctx, const uint8_t *d_bytes, g1_affine_t *d_out, int32_t *d_status, size_t count,
+                              int check_subgroup, size_t status_mod) {
+    CU(cudaEventRecord(ctx->ev_side_fork, ctx->cur->stream));
+    CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side_fork, 0));
+    k_decode_g1<<<blocks_for(count, 64), 64, 0, ctx->side_stream>>>(d_bytes, d_out, d_status, (uint32_t)count, check_subgroup,
+                                                                  (uint32_t)status_mod);
+    CU(cudaEventRecord(ctx->ev_side_join, ctx->side_stream));
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return KZG_B200_OK;
+}
 
 // ------------------------------------------------------------------ compute_blob_kzg_proof / compute_kzg_proof
 // One chunk on the device.  Exactly one of d_commitments (blob proof: z from the Fiat-Shamir
@@ -151,6 +165,7 @@ extern "C" int kzg_b200_compute_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t
 static int verify_phase_a_locked(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments, const uint8_t *proofs,
                                  size_t n, uint8_t *zy_out) {
     const size_t bpb = (size_t)ctx->n * 32, ch = ctx->chunk;
+    const size_t nchunks_total = (n + ch - 1) / ch;
     std::vector<int32_t> st(n);
     RC(staged_chunks(
         ctx, n,
@@ -167,7 +182,10 @@ static int verify_phase_a_locked(kzg_b200_ctx *ctx, const uint8_t *blobs, const 
             kzg_b200_ctx::Lane *ln = ctx->cur;
             cudaStream_t sm = ln->stream;
             CU(cudaMemsetAsync(d_st, 0, cnt * sizeof(int32_t), sm));
-            RC(decode_points(ctx, aux, ln->d_pts, d_st, 2 * cnt, 1, cnt));
+            // single-chunk calls validate the points beside the hash (profiling keeps the stages apart)
+            const bool side = nchunks_total == 1 && !ctx->profile;
+            if (side) RC(decode_points_side(ctx, aux, ln->d_pts, d_st, 2 * cnt, 1, cnt));
+            else RC(decode_points(ctx, aux, ln->d_pts, d_st, 2 * cnt, 1, cnt));
             stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
             k_challenge<<<blocks_for(cnt, 64), 64, 0, sm>>>(d_blobs, aux, (uint32_t)cnt, ctx->n, ln->d_z);
             stage_end(ctx, 1);
@@ -177,6 +195,7 @@ static int verify_phase_a_locked(kzg_b200_ctx *ctx, const uint8_t *blobs, const 
             stage_end(ctx, 1);
             ctx->launches += 2;
             CU(cudaGetLastError());
+            if (side) CU(cudaStreamWaitEvent(sm, ctx->ev_side_join, 0));
             CU(cudaMemcpyAsync(zy_out + off * 64, ln->d_zy, cnt * 64, cudaMemcpyDeviceToHost, sm));
             CU(cudaMemcpyAsync(st.data() + off, d_st, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, sm));
             return KZG_B200_OK;
@@ -221,8 +240,10 @@ extern "C" int kzg_b200_compute_r(const kzg_b200_ctx *ctx, const uint8_t *commit
 }
 
 // Phase B: the r-power linear combinations of one shard (reference src/kzg.rs:601-622).
+// d_pts_ready (optional): the 2n points phase A decoded on this context (commitments, then proofs)
 static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, const uint8_t *zy, const uint8_t *proofs,
-                                 size_t n, const uint8_t r[32], uint64_t first_index, uint8_t partial_out[224]) {
+                                 size_t n, const uint8_t r[32], uint64_t first_index, uint8_t partial_out[224],
+                                 const g1_affine_t *d_pts_ready = nullptr) {
     if (n == 0) {
         memset(partial_out, 0, 224);
         partial_out[0] = 0x40;
@@ -259,7 +280,8 @@ static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, 
     fr_t *sy = (fr_t *)(d + o_sy);
     CU(cudaMemsetAsync(d_st, 0, 2 * n * sizeof(int32_t), ctx->stream));
     // c and p byte arrays are contiguous: decode both with one launch (phase A did the subgroup checks)
-    RC(decode_points(ctx, d + o_c, pts, d_st, 2 * n, 0, 2 * n));
+    if (d_pts_ready) CU(cudaMemcpyAsync(pts, d_pts_ready, 2 * n * sizeof(g1_affine_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    else RC(decode_points(ctx, d + o_c, pts, d_st, 2 * n, 0, 2 * n));
     stage_begin(ctx, KZG_B200_STAGE_VERIFY_TERMS);
     k_verify_terms<<<blocks_for(3 * n, 96), 96, 0, ctx->stream>>>(pts, pts + n, d + o_zy, rc, first_index, (uint32_t)n, terms, sy);
     k_jac_sum<<<2, KZG_JSUM_THREADS, 0, ctx->stream>>>(terms, (uint32_t)n, sums);   // sums[0] = sum V_i, sums[1] = sum U_i
@@ -308,7 +330,8 @@ extern "C" int kzg_b200_verify_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const uin
     RC(verify_phase_a_locked(ctx, blobs, commitments, proofs, n, zy.data()));
     uint8_t r[32], partial[224];
     RC(kzg_b200_compute_r(ctx, commitments, zy.data(), proofs, n, r));
-    RC(verify_phase_b_locked(ctx, commitments, zy.data(), proofs, n, r, 0, partial));
+    // a single-chunk call still has phase A's decoded points in lane 0's workspace
+    RC(verify_phase_b_locked(ctx, commitments, zy.data(), proofs, n, r, 0, partial, n <= ctx->chunk ? ctx->lanes[0].d_pts : nullptr));
     return host_verify_finish(partial, 1, ctx->tau_prepared, ok) == 0 ? KZG_B200_OK : KZG_B200_BAD_ARGS;
 }
 
