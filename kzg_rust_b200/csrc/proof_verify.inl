@@ -37,12 +37,16 @@ static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t 
                        size_t count, uint8_t *d_proofs, uint8_t *d_zy, int32_t *d_status, const fr_t *d_z_ready = nullptr) {
     kzg_b200_ctx::Lane *ln = ctx->cur;
     cudaStream_t st = ln->stream;
+    bool side = false;
     if (d_z_ready) {
         // the caller validated the commitments (status already holds the verdicts) and hashed the challenges
         CU(cudaMemcpyAsync(ln->d_z, d_z_ready, count * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
     } else if (d_commitments) {
         CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), st));
-        RC(decode_points(ctx, d_commitments, ln->d_pts, d_status, count, 1, count));
+        // small calls: the commitment check runs on the side stream beside the challenge hash and the evaluation
+        side = count <= 256 && !ctx->profile;
+        if (side) RC(decode_points_side(ctx, d_commitments, ln->d_pts, d_status, count, 1, count));
+        else RC(decode_points(ctx, d_commitments, ln->d_pts, d_status, count, 1, count));
         {
             stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
             k_challenge<<<blocks_for(count, 64), 64, 0, st>>>(d_blobs, d_commitments, (uint32_t)count, ctx->n, ln->d_z);
@@ -61,6 +65,7 @@ static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t 
     CU(cudaGetLastError());
     const g1_affine_t *res = nullptr;
     RC(run_msm(ctx, count, &res));
+    if (side) CU(cudaStreamWaitEvent(st, ctx->ev_side_join, 0));  // the compression reads the status the check wrote
     stage_begin(ctx, KZG_B200_STAGE_COMPRESS);
     k_horner_compress<<<blocks_for(count, 64), 64, 0, st>>>(res, ctx->c, ctx->W, d_status, d_proofs, (uint32_t)count);
     stage_end(ctx, 1);
