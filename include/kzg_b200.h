@@ -111,6 +111,12 @@ int kzg_b200_compute_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, co
 int kzg_b200_verify_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments,
                                          const uint8_t *proofs, size_t n, int *ok);
 
+/* reference `Kzg::verify_kzg_proof` (src/kzg.rs:1039-1047 -> :429-445, :409-426): the proof that the
+ * polynomial behind `commitment` takes the value y at z.  BAD_ARGS for a z or y that is not a canonical
+ * field element, or a commitment / proof that is not a point of G1 (infinity is accepted). */
+int kzg_b200_verify_kzg_proof(kzg_b200_ctx *ctx, const uint8_t commitment[48], const uint8_t z[32],
+                              const uint8_t y[32], const uint8_t proof[48], int *ok);
+
 /*
  * Two-phase form of the batch verification for multi-GPU sharding.
  * Phase A (per shard): validate, z_i and y_i.  zy_out: n x 64 B (z_i || y_i, big-endian).

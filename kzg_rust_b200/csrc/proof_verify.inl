@@ -248,7 +248,7 @@ extern "C" int kzg_b200_compute_r(const kzg_b200_ctx *ctx, const uint8_t *commit
 // d_pts_ready (optional): the 2n points phase A decoded on this context (commitments, then proofs)
 static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, const uint8_t *zy, const uint8_t *proofs,
                                  size_t n, const uint8_t r[32], uint64_t first_index, uint8_t partial_out[224],
-                                 const g1_affine_t *d_pts_ready = nullptr) {
+                                 const g1_affine_t *d_pts_ready = nullptr, int check_subgroup = 0) {
     if (n == 0) {
         memset(partial_out, 0, 224);
         partial_out[0] = 0x40;
@@ -286,7 +286,7 @@ static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, 
     CU(cudaMemsetAsync(d_st, 0, 2 * n * sizeof(int32_t), ctx->stream));
     // c and p byte arrays are contiguous: decode both with one launch (phase A did the subgroup checks)
     if (d_pts_ready) CU(cudaMemcpyAsync(pts, d_pts_ready, 2 * n * sizeof(g1_affine_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    else RC(decode_points(ctx, d + o_c, pts, d_st, 2 * n, 0, 2 * n));
+    else RC(decode_points(ctx, d + o_c, pts, d_st, 2 * n, check_subgroup, 2 * n));
     stage_begin(ctx, KZG_B200_STAGE_VERIFY_TERMS);
     k_verify_terms<<<blocks_for(3 * n, 96), 96, 0, ctx->stream>>>(pts, pts + n, d + o_zy, rc, first_index, (uint32_t)n, terms, sy);
     k_jac_sum<<<2, KZG_JSUM_THREADS, 0, ctx->stream>>>(terms, (uint32_t)n, sums);   // sums[0] = sum V_i, sums[1] = sum U_i
@@ -337,6 +337,29 @@ extern "C" int kzg_b200_verify_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const uin
     RC(kzg_b200_compute_r(ctx, commitments, zy.data(), proofs, n, r));
     // a single-chunk call still has phase A's decoded points in lane 0's workspace
     RC(verify_phase_b_locked(ctx, commitments, zy.data(), proofs, n, r, 0, partial, n <= ctx->chunk ? ctx->lanes[0].d_pts : nullptr));
+    return host_verify_finish(partial, 1, ctx->tau_prepared, ok) == 0 ? KZG_B200_OK : KZG_B200_BAD_ARGS;
+}
+
+// reference verify_kzg_proof (src/kzg.rs:429-445 -> verify_kzg_proof_impl :409-426): no blob, the caller gives
+// z and the claimed y.  e(C - [y]G, G2) == e(proof, [tau - z]G2) is, for points of G1, the batch equation with
+// one term and r^0 = 1 -- e(proof, [tau]G2) == e(C - [y]G + [z]proof, G2) -- so phase B and the final check are
+// reused; here the points get their subgroup check in phase B because there is no phase A.
+extern "C" int kzg_b200_verify_kzg_proof(kzg_b200_ctx *ctx, const uint8_t commitment[48], const uint8_t z[32],
+                                         const uint8_t y[32], const uint8_t proof[48], int *ok) {
+    if (!ctx || !commitment || !z || !y || !proof || !ok) return KZG_B200_BAD_ARGS;
+    *ok = 0;
+    fr_t t;
+    scalar_from_be32(t, z);
+    if (!fr_is_canonical(t)) return KZG_B200_BAD_ARGS;  // bytes_to_bls_field, src/utils.rs:262-275
+    scalar_from_be32(t, y);
+    if (!fr_is_canonical(t)) return KZG_B200_BAD_ARGS;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    uint8_t zy[64], one[32] = {0}, partial[224];
+    memcpy(zy, z, 32);
+    memcpy(zy + 32, y, 32);
+    one[31] = 1;
+    RC(verify_phase_b_locked(ctx, commitment, zy, proof, 1, one, 0, partial, nullptr, 1));
     return host_verify_finish(partial, 1, ctx->tau_prepared, ok) == 0 ? KZG_B200_OK : KZG_B200_BAD_ARGS;
 }
 

@@ -92,6 +92,7 @@ def load_library():
     L.kzg_b200_synchronize.argtypes = [vp]
     L.kzg_b200_stream.argtypes = [vp]
     L.kzg_b200_stream.restype = vp
+    L.kzg_b200_verify_kzg_proof.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]
     L.kzg_b200_launch_count.argtypes = [vp]
     L.kzg_b200_launch_count.restype = ctypes.c_uint64
     L.kzg_b200_profile_enable.argtypes = [vp, ci]
@@ -334,6 +335,21 @@ class Kzg:
         if status[0]:
             _raise(int(status[0]), "compute_blob_kzg_proof")
         return KzgProof(out[0].tobytes())
+
+    @staticmethod
+    def verify_kzg_proof(commitment_bytes, z_bytes, y_bytes, proof_bytes, s):
+        """reference src/kzg.rs:1039-1047."""
+        L = load_library()
+        c, z, y, p = _raw(commitment_bytes), _raw(z_bytes), _raw(y_bytes), _raw(proof_bytes)
+        if len(c) != 48 or len(p) != 48:
+            raise InvalidBytesLength("Invalid byte length. Expected 48 got %d" % (len(c) if len(c) != 48 else len(p)))
+        if len(z) != 32 or len(y) != 32:
+            raise InvalidBytesLength("Invalid byte length. Expected 32 got %d" % (len(z) if len(z) != 32 else len(y)))
+        ok = ctypes.c_int(0)
+        rc = L.kzg_b200_verify_kzg_proof(s._h, bytes(c), bytes(z), bytes(y), bytes(p), ctypes.byref(ok))
+        if rc:
+            _raise(rc, "verify_kzg_proof")
+        return bool(ok.value)
 
     @staticmethod
     def verify_blob_kzg_proof(blob, commitment_bytes, proof_bytes, s):

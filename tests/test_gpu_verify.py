@@ -195,3 +195,26 @@ def test_config5_size_16384_blobs_round_trip_properties():
     exp_p, est = o.compute_blob_kzg_proof_many(blobs[idx], exp_c, nthreads=os.cpu_count() or 1)
     assert not est.any() and np.array_equal(prs[idx], exp_p)
     s.close()
+
+
+@pytest.mark.parametrize("case", G.by_fn("verify_kzg_proof"), ids=_ids("verify_kzg_proof"))
+def test_verify_kzg_proof_vectors(case):
+    """reference src/lib.rs:112-140: all 92 vectors (correct / incorrect proofs, points at infinity, z in and
+    out of the domain, non-canonical z / y, commitments and proofs off the curve or outside G1) through
+    kzg_b200_verify_kzg_proof -- phase B of the batch path with one term and the points subgroup-checked."""
+    k = _kzg()
+    s = gpu_settings("mainnet", 8)
+    try:
+        c = k.Bytes48.from_bytes(G.get_bytes(case["input"]["commitment"]))
+        z = k.Bytes32.from_bytes(G.get_bytes(case["input"]["z"]))
+        y = k.Bytes32.from_bytes(G.get_bytes(case["input"]["y"]))
+        p = k.Bytes48.from_bytes(G.get_bytes(case["input"]["proof"]))
+    except (k.Error, ValueError):
+        assert case["output"] is None
+        return
+    try:
+        ok = k.Kzg.verify_kzg_proof(c, z, y, p, s)
+    except k.Error:
+        assert case["output"] is None
+        return
+    assert ok is case["output"]
