@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(96) k_verify_terms(const g1_affine_t *__restri
     fe_from_mont(k, k);
     const g1_affine_t base_pt = role == 1 ? cpts[i] : ppts[i];
     g1_jac_t acc;
-    g1j_mul(acc, base_pt, k.l, 255);
+    g1j_mul_glv(acc, base_pt, k.l);
     out_pts[role == 0 ? i : count + 2 * i + (role - 1)] = acc;
 }
 // Each block adds a run of Jacobian points -> out[block] (affine): strided partial

@@ -186,6 +186,65 @@ KZG_HD void g1j_mul(g1_jac_t &r, const g1_affine_t &p, const uint32_t *k, int nb
     r = acc;
 }
 
+// [k]P for a full-width scalar with the G1 endomorphism psi(x, y) = (beta^2 x, y) = [lambda]P,
+// lambda = x^2 - 1 (x the curve parameter; lambda^2 + lambda + 1 = 0 mod r, 128 bits):
+//   k = k2 lambda + k1  (plain integer division, both halves below 2^128)
+//   [k]P = [k1]P + [k2]psi(P), one joint ladder of 128 doublings instead of 255,
+// and the third table entry is free: P + psi(P) = -psi^2(P) = (beta x, -y).
+// Used by the r-power terms of batch verification, whose latency is one such ladder per blob.
+KZG_HD void glv_split(uint32_t k1[4], uint32_t k2[4], const uint32_t k[8]) {
+    // lambda = BLS_X_SQUARED - 1
+    constexpr uint32_t xs[4] = {BLS_X_SQUARED_LIMBS};
+    const uint32_t lam[5] = {xs[0] - 1u, xs[1] - (xs[0] == 0 ? 1u : 0u), xs[2], xs[3], 0u};  // low limb of x^2 is 0: borrow into limb 1
+    uint32_t rem[5] = {0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+    for (int bit = 255; bit >= 0; bit--) {
+        // rem = 2 rem + bit  (rem < lambda before, so < 2^129 after)
+#pragma unroll
+        for (int i = 4; i > 0; i--) rem[i] = (rem[i] << 1) | (rem[i - 1] >> 31);
+        rem[0] = (rem[0] << 1) | ((k[bit >> 5] >> (bit & 31)) & 1u);
+        uint32_t d[5], cc = 0;
+        d[0] = sub_cc(rem[0], lam[0], cc);
+#pragma unroll
+        for (int i = 1; i < 5; i++) d[i] = subc_cc(rem[i], lam[i], cc);
+        uint32_t borrow = subc(0, 0, cc);
+        if (borrow == 0) {
+#pragma unroll
+            for (int i = 0; i < 5; i++) rem[i] = d[i];
+            q[bit >> 5] |= 1u << (bit & 31);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { k1[i] = rem[i]; k2[i] = q[i]; }  // q < 2^128 for k < 2^255 (r / lambda < 2^128)
+}
+KZG_HD void g1j_mul_glv(g1_jac_t &r, const g1_affine_t &p, const uint32_t *k) {
+    g1_jac_t acc;
+    g1j_set_inf(acc);
+    if (g1a_is_inf(p)) { r = acc; return; }
+    uint32_t k1[4], k2[4];
+    glv_split(k1, k2, k);
+    fp_t beta, x2, x3, yn;
+    {
+        constexpr uint32_t bm[12] = {FP_BETA_MONT_LIMBS};
+#pragma unroll
+        for (int i = 0; i < 12; i++) beta.l[i] = bm[i];
+    }
+    fe_mul(x3, p.x, beta);   // P + psi(P) = (beta x, -y)
+    fe_mul(x2, x3, beta);    // psi(P)     = (beta^2 x, y)
+    fe_neg(yn, p.y);
+#pragma unroll 1
+    for (int i = 127; i >= 0; i--) {
+        g1j_dbl(acc, acc);
+        uint32_t sel = ((k1[i >> 5] >> (i & 31)) & 1u) | (((k2[i >> 5] >> (i & 31)) & 1u) << 1);
+        if (sel) {
+            fp_t qx = sel == 1 ? p.x : (sel == 2 ? x2 : x3);
+            fp_t qy = sel == 3 ? yn : p.y;
+            g1j_add_affine(acc, acc, qx, qy);
+        }
+    }
+    r = acc;
+}
+
 // ------------------------------------------------------------------ serialisation
 // 48 big-endian bytes <-> 12 canonical limbs
 KZG_HD void fp_from_be48(fp_t &r, const uint8_t *b) {

@@ -79,3 +79,18 @@ extern "C" int shim_recode(const uint32_t *scalar, int c, int32_t *digits_out) {
     recode_signed(s, c, W, digits_out, 1);
     return W;
 }
+// [k]P by the plain ladder and by the GLV ladder (g1.cuh), both compressed; k = 8 little-endian words
+extern "C" int shim_g1_mul_both(const uint8_t *point48, const uint32_t *k, uint8_t *out_plain, uint8_t *out_glv, uint32_t *k1k2) {
+    g1_affine_t p;
+    if (!g1a_uncompress(p, point48)) return KZG_BADARGS;
+    g1_jac_t a, b;
+    g1j_mul(a, p, k, 256);
+    g1j_mul_glv(b, p, k);
+    g1_affine_t aa, bb;
+    g1j_to_affine(aa, a);
+    g1j_to_affine(bb, b);
+    g1a_compress(out_plain, aa);
+    g1a_compress(out_glv, bb);
+    glv_split(k1k2, k1k2 + 4, k);
+    return 0;
+}

@@ -269,3 +269,24 @@ def test_lazy_residues_vs_python(field):
         assert bool(field.shim_fp_is_zero_lazy(_limbs(v, 12))) == (v % P == 0)
         field.shim_fp_canonical(_limbs(v, 12), out)
         assert _val(out) == v % P
+
+
+def test_glv_scalar_multiplication_vs_plain_ladder_and_oracle(msm):
+    """g1j_mul_glv (k = k2 lambda + k1, joint 128-step ladder over P, psi(P), P + psi(P)) against the plain
+    255-step ladder of the same header and against the oracle's scalar multiplication."""
+    from oracle.binding import g1_lincomb
+    lam = 0xd201000000010000 ** 2 - 1
+    g = golden()
+    pts = [g.g1_bytes[48 * i:48 * i + 48] for i in (0, 1, 77, 4095)] + [b"\xc0" + bytes(47)]
+    rng = np.random.default_rng(21)
+    ks = [0, 1, 2, lam - 1, lam, lam + 1, 2 * lam, lam * lam % R, R - 1, R - 2, 2 ** 128 - 1, 2 ** 128, 2 ** 254] + \
+         [int.from_bytes(rng.bytes(32), "big") % R for _ in range(12)]
+    a, b = (ctypes.c_uint8 * 48)(), (ctypes.c_uint8 * 48)()
+    kk = (ctypes.c_uint32 * 8)()
+    for pt in pts:
+        for k in ks:
+            assert msm.shim_g1_mul_both(pt, _limbs(k, 8), a, b, kk) == 0
+            k1, k2 = _val(kk[0:4]), _val(kk[4:8])
+            assert k1 == k % lam and k2 == k // lam
+            assert bytes(a) == bytes(b), (k, pt[:4])
+            assert bytes(b) == g1_lincomb([pt], [k.to_bytes(32, "big")])
