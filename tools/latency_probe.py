@@ -1,5 +1,9 @@
+#!/usr/bin/env python3
+"""Per-stage device time and wall time of small calls (verify n = 1 and 6, one commitment, one proof) and of
+the host pairing check alone.  Not part of the product."""
 import ctypes, os, sys, time
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import kzg_rust_b200 as k
 from golden_util import golden
