@@ -240,6 +240,13 @@ template <class P> KZG_HD void fe_sub_lazy(Fe<P> &r, const Fe<P> &a, const Fe<P>
 #pragma unroll
     for (int i = 1; i < P::N; i++) r.l[i] = addc_cc(t.l[i], P::mod2(i) & borrow, c2);
 }
+// r = 2 mod - a for a in (0, 2 mod]: one carry chain where the canonical fe_neg takes three
+template <class P> KZG_HD void fe_neg_lazy(Fe<P> &r, const Fe<P> &a) {
+    uint32_t cc = 0;
+    r.l[0] = sub_cc(P::mod2(0), a.l[0], cc);
+#pragma unroll
+    for (int i = 1; i < P::N; i++) r.l[i] = subc_cc(P::mod2(i), a.l[i], cc);
+}
 // [0, 2 mod) -> [0, mod)
 template <class P> KZG_HD void fe_canonical(Fe<P> &a) { fe_reduce_once(a, 0); }
 // a == 0 (mod m) for a in [0, 2 mod): a is 0 or mod.  The low limb filters out all but 2^-31 of the values.

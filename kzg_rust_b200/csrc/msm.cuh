@@ -360,8 +360,9 @@ KZG_HD void batch_add_thread(const Policy &pol, uint64_t total, fp_t *scratch, i
             fp_t inv_j;
             fpx_mul<Policy::lazy>(inv_j, inv, pre);
             fpx_mul<Policy::lazy>(inv, inv, den);
-            if (ng1) fe_neg(p1.y, p1.y);
-            if (ng2) fe_neg(p2.y, p2.y);
+            // y of a table entry is canonical and never 0 (odd group order): 2p - y is a lazy residue
+            if (ng1) { if (Policy::lazy) fe_neg_lazy(p1.y, p1.y); else fe_neg(p1.y, p1.y); }
+            if (ng2) { if (Policy::lazy) fe_neg_lazy(p2.y, p2.y); else fe_neg(p2.y, p2.y); }
             add_finish<Policy::lazy>(r, kind, p1, p2, inv_j);
             g1_affine_t *o = pol.dst(g);
             st_fp(&o->x, r.x);
