@@ -240,6 +240,41 @@ template <class P> KZG_HD void fe_sub_lazy(Fe<P> &r, const Fe<P> &a, const Fe<P>
 #pragma unroll
     for (int i = 1; i < P::N; i++) r.l[i] = addc_cc(t.l[i], P::mod2(i) & borrow, c2);
 }
+// r = a - b + 2 mod with no condition at all: a, b in [0, 2 mod) give r in (0, 4 mod).  For differences that
+// only feed a product whose other factor is below 2 mod -- (4 mod)(2 mod)/R + mod < 2 mod for R > 8.2 mod (Fp:
+// R / mod = 9.8), and the accumulator of fe_mul_core stays below 5 mod 2^32 -- so the masked add-back of
+// fe_sub_lazy (12 of its 36 instructions) is not needed.  The difference may wrap below zero in between.
+template <class P> KZG_HD void fe_sub_lazy4(Fe<P> &r, const Fe<P> &a, const Fe<P> &b) {
+    uint32_t cc = 0;
+    Fe<P> t;
+    t.l[0] = sub_cc(a.l[0], b.l[0], cc);
+#pragma unroll
+    for (int i = 1; i < P::N; i++) t.l[i] = subc_cc(a.l[i], b.l[i], cc);
+    uint32_t c2 = 0;
+    r.l[0] = add_cc(t.l[0], P::mod2(0), c2);
+#pragma unroll
+    for (int i = 1; i < P::N; i++) r.l[i] = addc_cc(t.l[i], P::mod2(i), c2);
+}
+// a == 0 (mod m) for a in (0, 4 mod): a is mod, 2 mod or 3 mod; the low limb filters almost everything
+template <class P> KZG_HD bool fe_is_zero_lazy4(const Fe<P> &a) {
+    const uint32_t m0 = P::mod(0);
+    if (a.l[0] != m0 && a.l[0] != 2u * m0 && a.l[0] != 3u * m0) return false;
+    Fe<P> c = a;
+    // c in (0, 4 mod): bring it below 2 mod, then below mod
+    {
+        uint32_t d[P::N], cc = 0;
+        d[0] = sub_cc(c.l[0], P::mod2(0), cc);
+#pragma unroll
+        for (int i = 1; i < P::N; i++) d[i] = subc_cc(c.l[i], P::mod2(i), cc);
+        uint32_t borrow = subc(0, 0, cc);
+        if (borrow == 0) {
+#pragma unroll
+            for (int i = 0; i < P::N; i++) c.l[i] = d[i];
+        }
+    }
+    fe_canonical(c);
+    return fe_is_zero(c);
+}
 // r = 2 mod - a for a in (0, 2 mod]: one carry chain where the canonical fe_neg takes three
 template <class P> KZG_HD void fe_neg_lazy(Fe<P> &r, const Fe<P> &a) {
     uint32_t cc = 0;

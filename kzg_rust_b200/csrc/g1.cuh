@@ -44,8 +44,9 @@ template <bool LAZY, class LoadY1, class LoadY2>
 KZG_HD int add_denominator(fp_t &den, const fp_t &x1, const fp_t &x2, LoadY1 load_y1, LoadY2 load_y2) {
     if (fp_is_inf_marker(x1)) { den = fe_one<FpParams>(); return ADD_TAKE_P2; }
     if (fp_is_inf_marker(x2)) { den = fe_one<FpParams>(); return ADD_TAKE_P1; }
-    fpx_sub<LAZY>(den, x2, x1);
-    if (!(LAZY ? fe_is_zero_lazy(den) : fe_is_zero(den))) return ADD_GENERIC;
+    if (LAZY) fe_sub_lazy4(den, x2, x1);  // in (0, 4p): only ever multiplied by values below 2p
+    else fe_sub(den, x2, x1);
+    if (!(LAZY ? fe_is_zero_lazy4(den) : fe_is_zero(den))) return ADD_GENERIC;
     fp_t y1, y2;
     load_y1(y1);
     load_y2(y2);
@@ -68,14 +69,16 @@ KZG_HD void add_finish(g1_affine_t &r, int kind, const g1_affine_t &p1, const g1
         fe_dbl(num, t);
         fe_add(num, num, t);
     } else {
-        fpx_sub<LAZY>(num, p2.y, p1.y);
+        if (LAZY) fe_sub_lazy4(num, p2.y, p1.y);  // in (0, 4p), times inv < 2p
+        else fe_sub(num, p2.y, p1.y);
     }
     fpx_mul<LAZY>(lam, num, inv);
     fpx_mul<LAZY>(t, lam, lam);
     fpx_sub<LAZY>(t, t, p1.x);
     fpx_sub<LAZY>(t, t, p2.x);  // x3 (p2.x == p1.x mod p when doubling)
     fp_t u;
-    fpx_sub<LAZY>(u, p1.x, t);
+    if (LAZY) fe_sub_lazy4(u, p1.x, t);  // in (0, 4p), times lam < 2p
+    else fe_sub(u, p1.x, t);
     fpx_mul<LAZY>(u, lam, u);
     fpx_sub<LAZY>(r.y, u, p1.y);
     r.x = t;

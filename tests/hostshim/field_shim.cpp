@@ -66,3 +66,9 @@ void shim_fp_sub_lazy_many(const uint32_t *a, const uint32_t *b, uint32_t *r, si
 int shim_fp_is_zero_lazy(const uint32_t *a) { fp_t x; memcpy(x.l, a, 48); return fe_is_zero_lazy(x); }
 void shim_fp_canonical(const uint32_t *a, uint32_t *r) { fp_t x; memcpy(x.l, a, 48); fe_canonical(x); memcpy(r, x.l, 48); }
 }
+extern "C" {
+void shim_fp_sub_lazy4_many(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t count) {
+    for (size_t i = 0; i < count; i++) { fp_t x, y, z; memcpy(x.l, a + 12 * i, 48); memcpy(y.l, b + 12 * i, 48); fe_sub_lazy4(z, x, y); memcpy(r + 12 * i, z.l, 48); }
+}
+int shim_fp_is_zero_lazy4(const uint32_t *a) { fp_t x; memcpy(x.l, a, 48); return fe_is_zero_lazy4(x); }
+}

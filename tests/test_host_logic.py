@@ -290,3 +290,34 @@ def test_glv_scalar_multiplication_vs_plain_ladder_and_oracle(msm):
             assert k1 == k % lam and k2 == k // lam
             assert bytes(a) == bytes(b), (k, pt[:4])
             assert bytes(b) == g1_lincomb([pt], [k.to_bytes(32, "big")])
+
+
+def test_unconditional_lazy_subtraction_and_wide_products(field):
+    """fe_sub_lazy4 (a - b + 2p, no condition: result in (0, 4p)), its zero test, and fe_mul_lazy with one
+    factor below 4p and the other below 2p: congruent to the exact values and back below 2p."""
+    rng = np.random.default_rng(13)
+    edge = [0, 1, P - 1, P, P + 1, 2 * P - 1, (P - 1) // 2]
+    rand = [int.from_bytes(rng.bytes(49), "big") % (2 * P) for _ in range(400)]
+    av = rand + [e for e in edge for _ in edge]
+    bv = rand[::-1] + [e for _ in edge for e in edge]
+    n = len(av)
+    a, b = _pack(av, 12), _pack(bv, 12)
+    ptr = lambda x: x.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+    d = np.zeros((n, 12), dtype=np.uint32)
+    field.shim_fp_sub_lazy4_many(ptr(a), ptr(b), ptr(d), ctypes.c_size_t(n))
+    dv = _unpack(d)
+    assert all(0 < g < 4 * P for g in dv)
+    assert dv == [x - y + 2 * P for x, y in zip(av, bv)]
+    for g, x, y in list(zip(dv, av, bv))[:200] + list(zip(dv, av, bv))[-49:]:
+        assert bool(field.shim_fp_is_zero_lazy4(_limbs(g, 12))) == ((x - y) % P == 0)
+    for v in (P, 2 * P, 3 * P, P + 2 ** 32, 2 * P - 1):
+        assert bool(field.shim_fp_is_zero_lazy4(_limbs(v, 12))) == (v % P == 0)
+    Rinv = pow(pow(2, 384, P), -1, P)
+    wide = [min(4 * P - 1, 2 * x + 1) for x in av]        # up to 4p - 1
+    w = _pack(wide, 12)
+    r = np.zeros((n, 12), dtype=np.uint32)
+    for first, second, fv, sv in ((w, b, wide, bv), (b, w, bv, wide)):
+        field.shim_fp_mul_lazy_many(ptr(first), ptr(second), ptr(r), ctypes.c_size_t(n))
+        got = _unpack(r)
+        assert all(g < 2 * P for g in got)
+        assert [g % P for g in got] == [x * y * Rinv % P for x, y in zip(fv, sv)]
