@@ -161,8 +161,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         # NCCL_DEBUG=VERSION (set on some boxes) makes NCCL print a banner on stdout; rank 0 must print ONE JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE", "ABORT"):
+            os.environ["NCCL_DEBUG"] = "NONE"  # VERSION and WARN both print the banner (on stdout)
         dist.init_process_group("nccl", device_id=dev)
     L = k.load_library()
     g1, g2 = read_setup()

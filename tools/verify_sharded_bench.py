@@ -29,8 +29,8 @@ rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_R
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE", "ABORT"):
+        os.environ["NCCL_DEBUG"] = "NONE"  # VERSION and WARN both print the banner (on stdout)
     dist.init_process_group("nccl", device_id=dev)
 g = golden()
 L = k.load_library()
