@@ -34,7 +34,8 @@ static int decode_points_side(kzg_b200_ctx *ctx, const uint8_t *d_bytes, g1_affi
 // d_z_ready (optional): challenges of this chunk already computed (device-resident calls hash all blobs of
 // the call in one launch: a 4096-blob chunk alone is 28 SHA-256 streams per SM, which is latency-bound).
 static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments, const uint8_t *d_zbytes,
-                       size_t count, uint8_t *d_proofs, uint8_t *d_zy, int32_t *d_status, const fr_t *d_z_ready = nullptr) {
+                       size_t count, uint8_t *d_proofs, uint8_t *d_zy, int32_t *d_status, const fr_t *d_z_ready = nullptr,
+                       size_t off = 0, const DeferredCompress *dc = nullptr) {
     kzg_b200_ctx::Lane *ln = ctx->cur;
     cudaStream_t st = ln->stream;
     bool side = false;
@@ -66,12 +67,7 @@ static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t 
     const g1_affine_t *res = nullptr;
     RC(run_msm(ctx, count, &res));
     if (side) CU(cudaStreamWaitEvent(st, ctx->ev_side_join, 0));  // the compression reads the status the check wrote
-    stage_begin(ctx, KZG_B200_STAGE_COMPRESS);
-    k_horner_compress<<<blocks_for(count, 64), 64, 0, st>>>(res, ctx->c, ctx->W, d_status, d_proofs, (uint32_t)count);
-    stage_end(ctx, 1);
-    ctx->launches++;
-    CU(cudaGetLastError());
-    return KZG_B200_OK;
+    return compress_or_park(ctx, res, off, count, d_status, d_proofs, dc);
 }
 
 extern "C" int kzg_b200_compute_blob_kzg_proof_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments,
@@ -101,15 +97,18 @@ extern "C" int kzg_b200_compute_blob_kzg_proof_device(kzg_b200_ctx *ctx, const u
         CU(cudaGetLastError());
         d_z_all = ctx->d_z_all;
     }
+    DeferredCompress dc;
+    RC(deferred_begin(ctx, n, &dc));
     RC(lanes_begin(ctx));
     size_t i = 0;
     for (size_t off = 0; off < n; off += ctx->chunk, i++) {
         size_t cnt = std::min(ctx->chunk, n - off);
         lane_select(ctx, i);
         RC(proof_chunk(ctx, d_blobs + off * bpb, d_commitments + off * 48, nullptr, cnt, d_proofs_out + off * 48, nullptr,
-                       d_status + off, d_z_all ? d_z_all + off : nullptr));
+                       d_status + off, d_z_all ? d_z_all + off : nullptr, off, &dc));
     }
-    return lanes_end(ctx);
+    RC(lanes_end(ctx));
+    return deferred_finish(ctx, &dc, d_status, d_proofs_out);
 }
 
 extern "C" int kzg_b200_compute_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments,
