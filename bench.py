@@ -139,7 +139,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--blobs", type=int, default=int(os.environ.get("KZG_BENCH_BLOBS", 65536)), help="blobs per GPU per step")
     ap.add_argument("--host-pool", type=int, default=65536, help="pinned host blobs per end-to-end call (the user's batch; 8 GiB pinned at 65536)")
-    ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--comb-width", type=int, default=0, help="setup points per table group (0 = automatic)")
     ap.add_argument("--no-proof", action="store_true", help="skip the compute_blob_kzg_proof side measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -167,7 +167,7 @@ def main():
     L = k.load_library()
     g1, g2 = read_setup()
     t_create = time.time()
-    s = k.KzgSettings.load_trusted_setup(g1, g2, local_rank, args.window_bits)
+    s = k.KzgSettings.load_trusted_setup(g1, g2, local_rank, args.comb_width)
     t_create = time.time() - t_create
     stream = torch.cuda.ExternalStream(L.kzg_b200_stream(s._h), device=dev)
     B = args.blobs
@@ -314,8 +314,10 @@ def main():
     msm_launches = int(stage_ln[1] + stage_ln[2])
     blobs_timed = B  # the profiled step
     achieved = IMAD_PER_COMMIT * blobs_timed / (msm_ms * 1e-3) if msm_ms > 0 else 0.0
-    n_windows = {19: 14, 18: 15}.get(s.window_bits, -(-255 // s.window_bits))
-    executed_imad = n_windows * 4095 * 6 * 600.0
+    groups = -(-4096 // s.comb_width)
+    # what this design executes per blob: 255 bit positions x (groups - 1) affine additions x 6 products, plus the
+    # Horner pass (254 doublings at 7 products + 254 mixed additions at 11); 600 IMAD issue slots per product
+    executed_imad = (255 * (groups - 1) * 6 + 254 * 18) * 600.0
     wn = None
     roofline = {
         "bound": "imad", "kernel": "batch_add_kernel (GatherPolicy + TreePolicy launches)",
@@ -324,7 +326,7 @@ def main():
         # 4096-blob chunk at c = 19 (profiles/ncu_batch_add_r1c.md: 99.8 GB and 33.8 GB read + written);
         # levels 2..11 halve each time, 12 launches per chunk.  The MSM streams the selected table rows and the
         # intermediate levels through HBM by design (40 % of the HBM peak) to do 36 % fewer additions.
-        "traffic": (99.8e9 + 2 * 33.8e9) / 12 if s.window_bits == 19 else None,
+        "traffic": None,
         "traffic_unit": "DRAM bytes per average batch_add launch (ncu, 4096-blob chunk)",
         "launches": msm_launches, "avg_launch_ms": msm_ms / max(1, msm_launches),
         "algorithmic_imad_per_blob": IMAD_PER_COMMIT,
@@ -370,7 +372,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit Fp / 255-bit Fr integers)", "data": "synthetic",
         "config": {"workload": "mainnet blob_to_kzg_commitment, %d synthetic blobs per GPU per step (BASELINE.json configs[3]), "
                                "trusted_setup.txt" % B,
-                   "blobs_per_gpu_per_step": B, "window_bits": s.window_bits, "sharding": "independent blobs, one context per GPU, no collective",
+                   "blobs_per_gpu_per_step": B, "comb_width": s.comb_width, "table_gb": round(s.table_bytes / 1e9, 1), "chunk_blobs": s.chunk_blobs, "sharding": "independent blobs, one context per GPU, no collective",
                    "l2": "inputs (%.1f GiB per step) exceed L2" % (B * BYTES_PER_BLOB / 2 ** 30), "ctx_create_s": round(t_create, 2)},
         "e2e": {"value": e2e_value, "unit": "blobs/s", "h2d_bytes_per_step": calls * pool * BYTES_PER_BLOB,
                 "d2h_bytes_per_step": calls * pool * 52, "ms_per_step": e2e_ms / args.steps,

@@ -61,23 +61,28 @@ typedef struct kzg_b200_ctx kzg_b200_ctx;
  *   g2_monomial: n2 x 96 B compressed G2 points; n2 must be 65
  *   n1:          FIELD_ELEMENTS_PER_BLOB of the preset: 4096 (kzg_mainnet) or 4 (kzg_minimal)
  *   device:      CUDA device ordinal
- *   window_bits: signed-digit window c of the precomputed table (n1 x 2^(c-1) affine points of
- *                96 B), 2..20; 0 = pick the largest that fits the device's free memory
- *                (19 on an empty 180 GB B200: 14 windows, 103 GB of table; 18: 51.5 GB)
+ *   comb_width:  g, the number of setup points whose signed sums one table group holds (ceil(n1/g) groups of
+ *                2^(g-1) affine points of 96 B); a commitment costs 255 x (ceil(n1/g) - 1) point additions.
+ *                1..24; 0 = the widest comb whose table takes at most half of the device's free memory and
+ *                leaves room for the workspace (23 on an empty 180 GB B200: 72 GB of table; 22: 38 GB, 4.5 % more
+ *                additions; 20: 10 GB, 15 % more)
  */
 int kzg_b200_ctx_create(const uint8_t *g1_lagrange, size_t n1, const uint8_t *g2_monomial, size_t n2,
-                        int device, int window_bits, kzg_b200_ctx **out);
+                        int device, int comb_width, kzg_b200_ctx **out);
 
 /* Replaces `Kzg::load_trusted_setup_file` (src/kzg.rs:995-999 -> :906-979): text file
  * "n1\nn2\n" followed by n1 + n2 hex lines. */
-int kzg_b200_ctx_create_from_file(const char *path, int device, int window_bits, kzg_b200_ctx **out);
+int kzg_b200_ctx_create_from_file(const char *path, int device, int comb_width, kzg_b200_ctx **out);
 
 void kzg_b200_ctx_destroy(kzg_b200_ctx *ctx);
 
 /* FIELD_ELEMENTS_PER_BLOB of the context's preset (src/consts.rs:13). */
 size_t kzg_b200_field_elements_per_blob(const kzg_b200_ctx *ctx);
-/* Signed-digit window width the context's table was built with. */
-int kzg_b200_window_bits(const kzg_b200_ctx *ctx);
+/* Comb width g the context's table was built with, the table's size in bytes, and the number of blobs the
+ * context works on at a time (batched calls of any size are cut into chunks of this many). */
+int kzg_b200_comb_width(const kzg_b200_ctx *ctx);
+size_t kzg_b200_table_bytes(const kzg_b200_ctx *ctx);
+size_t kzg_b200_chunk_blobs(const kzg_b200_ctx *ctx);
 
 /*
  * Replaces `Kzg::blob_to_kzg_commitment` (src/kzg.rs:1013-1018 -> :401-406), batched.
@@ -141,6 +146,7 @@ int kzg_b200_verify_finish(const kzg_b200_ctx *ctx, const uint8_t *partials, siz
  * Device-resident forms (inputs and outputs already in this context's GPU memory; used by
  * pipelines that produce blobs on the device and by bench.py's HBM-resident measurement).
  * Asynchronous on the context's stream; kzg_b200_synchronize waits for completion.
+ * The device pointers must be 16-byte aligned (they are read with 128-bit loads): KZG_B200_BAD_ARGS otherwise.
  */
 int kzg_b200_blob_to_kzg_commitment_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, size_t n, uint8_t *d_out,
                                            int32_t *d_status);
@@ -154,7 +160,7 @@ int kzg_b200_synchronize(kzg_b200_ctx *ctx);
  * stage since then (arrays of KZG_B200_NUM_STAGES).
  */
 enum {
-    KZG_B200_STAGE_DIGITS = 0,       /* blob bytes -> canonical check -> signed window digits */
+    KZG_B200_STAGE_DIGITS = 0,       /* blob bytes -> canonical check -> sign words -> comb digits */
     KZG_B200_STAGE_MSM_GATHER = 1,   /* first level of the MSM: table gather + batched affine additions */
     KZG_B200_STAGE_MSM_TREE = 2,     /* remaining levels of the addition tree */
     KZG_B200_STAGE_COMPRESS = 3,     /* 48-byte compression */
@@ -184,10 +190,18 @@ int kzg_b200_measure_peaks(kzg_b200_ctx *ctx, double *imad_per_s, double *imad_w
 
 /* Test aids (tests/test_gpu_field.py, tests/test_gpu_commit.py): device field arithmetic on arrays of raw
  * limbs -- op 0: Fp mul, 1: Fp inverse, 2: Fr mul (8 words per element, all others 12), 3: Fp add, 4: Fp sub,
- * 5 / 6: Fp mul / square with the product formed on the FP64 pipe (csrc/fp_hybrid.cuh), 7 / 8: Fp mul / sub
- * on lazy residues in [0, 2p) (what the MSM levels use) -- and a read-back of precomputed table entries. */
+ * 7 / 8: Fp mul / sub on lazy residues in [0, 2p) (what the MSM levels use) -- and a read-back of precomputed
+ * table entries (flat index: group q, entry idx -> q * 2^(g-1) + idx; 96 B each, affine Montgomery limbs). */
 int kzg_b200_debug_field_op(kzg_b200_ctx *ctx, int op, const uint32_t *a, const uint32_t *b, uint32_t *out, uint64_t count);
 int kzg_b200_debug_table(kzg_b200_ctx *ctx, uint64_t first, uint64_t count, void *out);
+/*
+ * Whole-batch identity check for setups whose secret is public (the bundled testing setup: tau = 1337, SURVEY.md
+ * section 8c): d_ok[i] = (commitment_i == [p_i(tau)] G1), where p_i(tau) comes from the evaluation kernel and
+ * [y]G1 from a plain double-and-add ladder on the generator -- no part of the MSM is on that side.  Device
+ * pointers (16-byte aligned), n x int32 out; synchronous.  bench.py checks every commitment of the timed batch with it.
+ */
+int kzg_b200_debug_check_tau_identity(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments, size_t n,
+                                      const uint8_t tau[32], int32_t *d_ok);
 
 #ifdef __cplusplus
 }

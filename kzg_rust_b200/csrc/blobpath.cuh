@@ -50,60 +50,107 @@ KZG_HD void scalar_reduce(fr_t &a) {
     }
 }
 
-// Number of signed c-bit windows needed for any scalar s < r: ceil(255/c), plus one when
-// the top window of r-1 (plus an incoming carry) could exceed 2^(c-1).  c = 15 -> 17.
-inline int msm_num_windows(int c) {
-    const uint32_t rm[8] = {FR_R_LIMBS};
-    int W = (255 + c - 1) / c;
-    int bit = c * (W - 1);
-    uint64_t top = 0;  // (r-1) >> bit; r is odd so r-1 only clears bit 0, irrelevant unless bit == 0
-    for (int k = 0; k < 32 && bit + k < 256; k++) top |= (uint64_t)((rm[(bit + k) >> 5] >> ((bit + k) & 31)) & 1) << k;
-    if (top + 1 > (1ull << (c - 1))) W++;
-    return W;
+// ------------------------------------------------------------------ signed comb recoding of the scalars
+// The MSM (msm.cuh) looks up precomputed signed sums of g setup points,
+//     T[q][idx] = P_{q,0} + sum_{k=1..g-1} (bit_{k-1}(idx) ? + : -) P_{q,k},      P_{q,k} = G_{q g + k},
+// one lookup per (group q, bit position j) -- so every scalar is first written with digits +-1 only:
+//     s = sum_{j=0..254} e_j 2^j  (mod r),   e_j in {+1, -1}.
+// For an odd s < 2^255 that is e_j = +1 iff bit j+1 of s is set (j < 254), e_254 = +1.  An even s
+// (zero included) is replaced by r - s, which is odd and in [1, r], with every sign flipped.
+// The 255 signs of a scalar are its "sign words" (bit j set = plus), 8 x 32 bits.
+#define KZG_COMB_WINDOWS 255
+#define KZG_COMB_MAX_WIDTH 24
+KZG_HD void scalar_sign_words(uint32_t out[8], const fr_t &s) {
+    const uint32_t flip = (s.l[0] & 1u) ? 0u : 0xffffffffu;
+    uint32_t t[8], cc = 0;
+    // t = flip ? r - s : s
+    t[0] = sub_cc(FrParams::mod(0), s.l[0], cc);
+#pragma unroll
+    for (int i = 1; i < 8; i++) t[i] = subc_cc(FrParams::mod(i), s.l[i], cc);
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = flip ? t[i] : s.l[i];
+    // (t - 1) / 2 + 2^254, then the flip
+#pragma unroll
+    for (int i = 0; i < 7; i++) out[i] = ((t[i] >> 1) | (t[i + 1] << 31)) ^ flip;
+    out[7] = ((t[7] >> 1) | 0x40000000u) ^ (flip & 0x7fffffffu);
 }
-
-// Signed c-bit digits of a canonical scalar s < r:  s = sum_j d_j 2^(c j), |d_j| <= 2^(c-1),
-// W = msm_num_windows(c) so the top window never carries out.  Digit j goes to out[j*stride].
-KZG_HD void recode_signed(const fr_t &s, int c, int W, int32_t *out, uint64_t stride) {
-    const uint32_t mask = (1u << c) - 1u, half = 1u << (c - 1);
-    uint32_t carry = 0;
-#pragma unroll 1
-    for (int j = 0; j < W; j++) {
-        int bit = j * c;
-        int w = bit >> 5, sh = bit & 31;
-        uint64_t lo = w < 8 ? s.l[w] : 0u, hi = (w + 1) < 8 ? s.l[w + 1] : 0u;
-        uint32_t v = (uint32_t)(((hi << 32) | lo) >> sh) & mask;
-        v += carry;
-        int d;
-        if (v > half) { d = (int)v - (int)(1u << c); carry = 1; } else { d = (int)v; carry = 0; }
-        out[(uint64_t)j * stride] = d;
+// g sign bits of one (group, bit position) pair, bit k = point k of the group  ->  table index and sign:
+// the table only holds the half with +P_{q,0}; the other half is its negation.  Bit 31 = negate.
+KZG_HD uint32_t comb_digit(uint32_t pattern, int g) {
+    const uint32_t full = (1u << g) - 1u;  // g <= KZG_COMB_MAX_WIDTH
+    const uint32_t neg = (~pattern) & 1u;
+    if (neg) pattern = ~pattern & full;
+    return ((pattern & full) >> 1) | (neg << 31);
+}
+// 32 x 32 bit-matrix transpose in place: afterwards bit j of a[i] is what bit i of a[j] was
+// (the butterfly of Hacker's Delight 7-3, 5 rounds of 16 swaps).
+KZG_HD void transpose32(uint32_t a[32]) {
+    uint32_t m = 0x0000ffffu;
+#pragma unroll
+    for (int j = 16; j != 0; j >>= 1, m ^= (m << j)) {
+#pragma unroll
+        for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
+            uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
+            a[k] ^= t << j;
+            a[k + j] ^= t;
+        }
     }
 }
 
-// One blob element: range check + digits.  Non-canonical elements mark the blob BADARGS
-// (reference src/utils.rs:266-270) and contribute zero digits.
-KZG_HD void blob_digits_thread(const uint8_t *blobs, uint64_t e, int n, int c, int W, int32_t *digits, int *status) {
-    uint64_t b = e / (uint64_t)n;
-    uint32_t i = (uint32_t)(e - b * n);
+// One blob element -> its sign words, with the range check of `bytes_to_bls_field` (reference
+// src/utils.rs:262-275): a non-canonical element marks the blob BADARGS and counts as zero.
+// sign_words layout: [blob][word w][point i], n_pad points per row (the padding points of the last group are
+// points at infinity: their signs do not matter).
+KZG_HD void blob_sign_words_thread(const uint8_t *blobs, uint64_t e, int n, int n_pad, uint32_t *sign_words, int *status) {
+    uint64_t b = e / (uint64_t)n_pad;
+    uint32_t i = (uint32_t)(e - b * n_pad);
     fr_t s;
-    scalar_from_be32(s, blobs + e * 32);
-    if (!fr_is_canonical(s)) {
+    fe_set_zero(s);
+    if (i < (uint32_t)n) {
+        scalar_from_be32(s, blobs + (b * n + i) * 32);
+        if (!fr_is_canonical(s)) {
 #if defined(__CUDA_ARCH__)
-        atomicMax(status + b, (int)KZG_BADARGS);
+            atomicMax(status + b, (int)KZG_BADARGS);
 #else
-        status[b] = KZG_BADARGS;
+            status[b] = KZG_BADARGS;
 #endif
-        fe_set_zero(s);
+            fe_set_zero(s);
+        }
     }
-    recode_signed(s, c, W, digits + (b * W) * (uint64_t)n + i, (uint64_t)n);
+    uint32_t w[8];
+    scalar_sign_words(w, s);
+#pragma unroll
+    for (int k = 0; k < 8; k++) sign_words[(b * 8 + k) * (uint64_t)n_pad + i] = w[k];
 }
-// Same, from an Fr element in Montgomery form (the quotient polynomial of a proof).
-KZG_HD void fr_digits_thread(const fr_t *evals, uint64_t e, int n, int c, int W, int32_t *digits) {
-    uint64_t b = e / (uint64_t)n;
-    uint32_t i = (uint32_t)(e - b * n);
+// Same from canonical little-endian limbs (the quotient polynomial of a proof), scalars[b*n + i].
+KZG_HD void fr_sign_words_thread(const fr_t *scalars, uint64_t e, int n, int n_pad, uint32_t *sign_words) {
+    uint64_t b = e / (uint64_t)n_pad;
+    uint32_t i = (uint32_t)(e - b * n_pad);
     fr_t s;
-    fe_from_mont(s, evals[e]);
-    recode_signed(s, c, W, digits + (b * W) * (uint64_t)n + i, (uint64_t)n);
+    fe_set_zero(s);
+    if (i < (uint32_t)n) s = scalars[b * n + i];
+    uint32_t w[8];
+    scalar_sign_words(w, s);
+#pragma unroll
+    for (int k = 0; k < 8; k++) sign_words[(b * 8 + k) * (uint64_t)n_pad + i] = w[k];
+}
+// Digits of (blob b, group q): for every bit position j the g sign bits of the group's points, as table index + sign.
+//   digits[(q*255 + j)*count + b]   (group-major, what the gather level of the MSM reads, coalesced in b)
+KZG_HD void comb_index_thread(const uint32_t *sign_words, uint32_t b, uint32_t q, int g, int n_pad, uint32_t count,
+                              uint32_t *digits) {
+#pragma unroll 1
+    for (int w = 0; w < 8; w++) {
+        const uint32_t *row = sign_words + ((uint64_t)b * 8 + w) * (uint64_t)n_pad + (uint64_t)q * g;
+        uint32_t a[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) a[k] = k < g ? row[k] : 0u;
+        transpose32(a);  // a[t] bit k = sign of point k at bit position 32 w + t
+#pragma unroll
+        for (int t = 0; t < 32; t++) {
+            const int j = 32 * w + t;
+            if (j < KZG_COMB_WINDOWS) digits[((uint64_t)q * KZG_COMB_WINDOWS + j) * count + b] = comb_digit(a[t], g);
+        }
+    }
 }
 
 // Horner pass over the W window sums of one blob: sum_j 2^(c j) S_j, S_j affine (possibly

@@ -152,14 +152,13 @@ __global__ void k_load_scalars(const uint8_t *__restrict__ in, uint32_t count, f
 // products, a block-wide prefix and suffix scan of the per-thread totals, one field
 // inversion, and the unwinding.  inv[] (n per blob, global, L2-resident) holds the prefix
 // products and then the inverses.  QUOT = false stops after y (verification).
-// Outputs: zy_out (optional) = z || y as 32-byte big-endian records; digits (QUOT) = signed
-// window digits of the canonical q_i, ready for the MSM.
+// Outputs: zy_out (optional) = z || y as 32-byte big-endian records; with QUOT the canonical q_i
+// replace the inverses in inv[], ready for the recoding of the MSM (msm_digits_from_scalars).
 #define KZG_EVAL_THREADS 256
 template <bool QUOT>
 __global__ void __launch_bounds__(KZG_EVAL_THREADS) k_eval_quotient(
     const uint8_t *__restrict__ blobs, const fr_t *__restrict__ z_canon, const fr_t *__restrict__ roots, int n,
-    fr_t *__restrict__ inv, fr_t *__restrict__ poly, uint8_t *__restrict__ zy_out, int32_t *__restrict__ digits, int c,
-    int W, int32_t *status) {
+    fr_t *__restrict__ inv, fr_t *__restrict__ poly, uint8_t *__restrict__ zy_out, int32_t *status) {
     constexpr int T = KZG_EVAL_THREADS;
     __shared__ fr_t sh_pre[2][T];
     __shared__ fr_t sh_suf[2][T];
@@ -270,7 +269,6 @@ __global__ void __launch_bounds__(KZG_EVAL_THREADS) k_eval_quotient(
     __syncthreads();
     if (!QUOT) return;
     const fr_t y = sh_val[1];
-    int32_t *bdig = digits + (size_t)b * W * n;
     fe_set_zero(acc);
 #pragma unroll 1
     for (int i = tid; i < n; i += T) {
@@ -286,7 +284,7 @@ __global__ void __launch_bounds__(KZG_EVAL_THREADS) k_eval_quotient(
             fe_mul(t, q, w);      // = -(p_i - y) w_i / d_i
             fe_sub(acc, acc, t);
         }
-        recode_signed(q, c, W, bdig + i, (uint64_t)n);  // q is the canonical q_i
+        st_fr(binv + i, q);  // q is the canonical q_i
     }
     if (m >= 0) {  // uniform per CTA
         __syncthreads();
@@ -301,7 +299,7 @@ __global__ void __launch_bounds__(KZG_EVAL_THREADS) k_eval_quotient(
             fr_t zi, q;
             fr_inv(zi, z);  // z = w_m != 0
             fe_mul(q, red[0], zi);
-            recode_signed(q, c, W, bdig + m, (uint64_t)n);
+            st_fr(binv + m, q);
         }
     }
 }

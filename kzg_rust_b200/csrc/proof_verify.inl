@@ -5,25 +5,21 @@
 static int decode_points(kzg_b200_ctx *ctx, const uint8_t *d_bytes, g1_affine_t *d_out, int32_t *d_status, size_t count,
                          int check_subgroup, size_t status_mod) {
     stage_begin(ctx, KZG_B200_STAGE_VALIDATE);
-    k_decode_g1<<<blocks_for(count, 64), 64, 0, ctx->cur->stream>>>(d_bytes, d_out, d_status, (uint32_t)count, check_subgroup,
-                                                               (uint32_t)status_mod);
+    int rc = g1_launch_decode(ctx->cur->stream, d_bytes, d_out, d_status, count, check_subgroup, status_mod);
     stage_end(ctx, 1);
     ctx->launches++;
-    CU(cudaGetLastError());
-    return KZG_B200_OK;
+    return rc;
 }
 // The same on the context's side stream, forked from and joined to the current lane's stream by the caller:
-// small verification calls are chains of latency-bound kernels, and decompression + subgroup checks (2.2 ms)
-// do not depend on the challenge hash (3.1 ms) that runs meanwhile.
+// small verification calls are chains of latency-bound kernels, and decompression + subgroup checks
+// do not depend on the challenge hash that runs meanwhile.
 static int decode_points_side(kzg_b200_ctx *ctx, const uint8_t *d_bytes, g1_affine_t *d_out, int32_t *d_status, size_t count,
                               int check_subgroup, size_t status_mod) {
     CU(cudaEventRecord(ctx->ev_side_fork, ctx->cur->stream));
     CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side_fork, 0));
-    k_decode_g1<<<blocks_for(count, 64), 64, 0, ctx->side_stream>>>(d_bytes, d_out, d_status, (uint32_t)count, check_subgroup,
-                                                                  (uint32_t)status_mod);
+    RC(g1_launch_decode(ctx->side_stream, d_bytes, d_out, d_status, count, check_subgroup, status_mod));
     CU(cudaEventRecord(ctx->ev_side_join, ctx->side_stream));
     ctx->launches++;
-    CU(cudaGetLastError());
     return KZG_B200_OK;
 }
 
@@ -48,24 +44,23 @@ static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t 
         side = count <= 256 && !ctx->profile;
         if (side) RC(decode_points_side(ctx, d_commitments, ln->d_pts, d_status, count, 1, count));
         else RC(decode_points(ctx, d_commitments, ln->d_pts, d_status, count, 1, count));
-        {
-            stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
-            k_challenge<<<blocks_for(count, 64), 64, 0, st>>>(d_blobs, d_commitments, (uint32_t)count, ctx->n, ln->d_z);
-            stage_end(ctx, 1);
-        }
+        stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
+        int rc = fr_launch_challenge(st, d_blobs, d_commitments, count, ctx->n, ln->d_z);
+        stage_end(ctx, 1);
+        RC(rc);
     } else {
         CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), st));
-        k_load_scalars<<<blocks_for(count, 128), 128, 0, st>>>(d_zbytes, (uint32_t)count, ln->d_z, d_status);
+        RC(fr_launch_load_scalars(st, d_zbytes, count, ln->d_z, d_status));
     }
     ctx->launches++;
     stage_begin(ctx, KZG_B200_STAGE_EVAL);
-    k_eval_quotient<true><<<(unsigned)count, KZG_EVAL_THREADS, 0, st>>>(
-        d_blobs, ln->d_z, ctx->d_roots, ctx->n, ln->d_inv, ln->d_poly, d_zy, ln->d_digits, ctx->c, ctx->W, d_status);
+    int rc = fr_launch_eval(st, 1, d_blobs, ln->d_z, ctx->d_roots, ctx->n, ln->d_inv, ln->d_poly, d_zy, d_status, count);
     stage_end(ctx, 1);
     ctx->launches++;
-    CU(cudaGetLastError());
+    RC(rc);
+    RC(msm_digits_from_scalars(ctx, ln->d_inv, count));  // the quotient, canonical, where the inverses were
     const g1_affine_t *res = nullptr;
-    RC(run_msm(ctx, count, &res));
+    RC(msm_run(ctx, count, &res));
     if (side) CU(cudaStreamWaitEvent(st, ctx->ev_side_join, 0));  // the compression reads the status the check wrote
     return compress_or_park(ctx, res, off, count, d_status, d_proofs, dc);
 }
@@ -73,6 +68,7 @@ static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t 
 extern "C" int kzg_b200_compute_blob_kzg_proof_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments,
                                                       size_t n, uint8_t *d_proofs_out, int32_t *d_status) {
     if (!ctx || (n && (!d_blobs || !d_commitments || !d_proofs_out || !d_status))) return KZG_B200_BAD_ARGS;
+    if (!aligned16(d_blobs) || !aligned16(d_commitments) || !aligned16(d_proofs_out)) return KZG_B200_BAD_ARGS;
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     const size_t bpb = (size_t)ctx->n * 32;
@@ -91,10 +87,10 @@ extern "C" int kzg_b200_compute_blob_kzg_proof_device(kzg_b200_ctx *ctx, const u
         CU(cudaMemsetAsync(d_status, 0, n * sizeof(int32_t), ctx->stream));
         RC(decode_points(ctx, d_commitments, reinterpret_cast<g1_affine_t *>(ctx->d_z_all + n), d_status, n, 1, n));
         stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
-        k_challenge<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(d_blobs, d_commitments, (uint32_t)n, ctx->n, ctx->d_z_all);
+        int rc = fr_launch_challenge(ctx->stream, d_blobs, d_commitments, n, ctx->n, ctx->d_z_all);
         stage_end(ctx, 1);
         ctx->launches++;
-        CU(cudaGetLastError());
+        RC(rc);
         d_z_all = ctx->d_z_all;
     }
     DeferredCompress dc;
@@ -191,14 +187,14 @@ static int verify_phase_a_locked(kzg_b200_ctx *ctx, const uint8_t *blobs, const 
             if (side) RC(decode_points_side(ctx, aux, ln->d_pts, d_st, 2 * cnt, 1, cnt));
             else RC(decode_points(ctx, aux, ln->d_pts, d_st, 2 * cnt, 1, cnt));
             stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
-            k_challenge<<<blocks_for(cnt, 64), 64, 0, sm>>>(d_blobs, aux, (uint32_t)cnt, ctx->n, ln->d_z);
+            int rc = fr_launch_challenge(sm, d_blobs, aux, cnt, ctx->n, ln->d_z);
             stage_end(ctx, 1);
+            RC(rc);
             stage_begin(ctx, KZG_B200_STAGE_EVAL);
-            k_eval_quotient<false><<<(unsigned)cnt, KZG_EVAL_THREADS, 0, sm>>>(
-                d_blobs, ln->d_z, ctx->d_roots, ctx->n, ln->d_inv, ln->d_poly, ln->d_zy, nullptr, ctx->c, ctx->W, d_st);
+            rc = fr_launch_eval(sm, 0, d_blobs, ln->d_z, ctx->d_roots, ctx->n, ln->d_inv, ln->d_poly, ln->d_zy, d_st, cnt);
             stage_end(ctx, 1);
             ctx->launches += 2;
-            CU(cudaGetLastError());
+            RC(rc);
             if (side) CU(cudaStreamWaitEvent(sm, ctx->ev_side_join, 0));
             CU(cudaMemcpyAsync(zy_out + off * 64, ln->d_zy, cnt * 64, cudaMemcpyDeviceToHost, sm));
             CU(cudaMemcpyAsync(st.data() + off, d_st, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, sm));
@@ -287,16 +283,11 @@ static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, 
     if (d_pts_ready) CU(cudaMemcpyAsync(pts, d_pts_ready, 2 * n * sizeof(g1_affine_t), cudaMemcpyDeviceToDevice, ctx->stream));
     else RC(decode_points(ctx, d + o_c, pts, d_st, 2 * n, check_subgroup, 2 * n));
     stage_begin(ctx, KZG_B200_STAGE_VERIFY_TERMS);
-    k_verify_terms<<<blocks_for(3 * n, 96), 96, 0, ctx->stream>>>(pts, pts + n, d + o_zy, rc, first_index, (uint32_t)n, terms, sy);
-    k_jac_sum<<<2, KZG_JSUM_THREADS, 0, ctx->stream>>>(terms, (uint32_t)n, sums);   // sums[0] = sum V_i, sums[1] = sum U_i
-    stage_end(ctx, 2);
-    ctx->launches += 2;
-    CU(cudaGetLastError());
-    const g1_affine_t *in = sums;
-    k_fr_sum<<<1, 256, 0, ctx->stream>>>(sy, (uint32_t)n, sy + n);
-    k_write_partial<<<1, 32, 0, ctx->stream>>>(in, sy + n, d + o_part);
-    ctx->launches += 2;
-    CU(cudaGetLastError());
+    int lrc = fr_launch_verify_terms(ctx->stream, pts, pts + n, d + o_zy, rc, first_index, n, terms, sy);
+    if (lrc == KZG_B200_OK) lrc = fr_launch_verify_sums(ctx->stream, terms, sy, n, sums, sy + n, d + o_part);
+    stage_end(ctx, 4);
+    ctx->launches += 4;
+    RC(lrc);
     std::vector<int32_t> st(2 * n);
     CU(cudaMemcpyAsync(st.data(), d_st, 2 * n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(partial_out, d + o_part, 224, cudaMemcpyDeviceToHost, ctx->stream));

@@ -78,7 +78,12 @@ def load_library():
     L.kzg_b200_ctx_destroy.restype = None
     L.kzg_b200_field_elements_per_blob.argtypes = [vp]
     L.kzg_b200_field_elements_per_blob.restype = sz
-    L.kzg_b200_window_bits.argtypes = [vp]
+    L.kzg_b200_comb_width.argtypes = [vp]
+    L.kzg_b200_table_bytes.argtypes = [vp]
+    L.kzg_b200_table_bytes.restype = sz
+    L.kzg_b200_chunk_blobs.argtypes = [vp]
+    L.kzg_b200_chunk_blobs.restype = sz
+    L.kzg_b200_debug_check_tau_identity.argtypes = [vp, vp, vp, sz, cp, vp]
     L.kzg_b200_blob_to_kzg_commitment_batch.argtypes = [vp, vp, sz, vp, vp]
     L.kzg_b200_compute_blob_kzg_proof_batch.argtypes = [vp, vp, vp, sz, vp, vp]
     L.kzg_b200_compute_kzg_proof_batch.argtypes = [vp, vp, vp, sz, vp, vp, vp]
@@ -189,10 +194,12 @@ class KzgSettings:
         L = load_library()
         self.field_elements_per_blob = L.kzg_b200_field_elements_per_blob(handle)
         self.bytes_per_blob = 32 * self.field_elements_per_blob
-        self.window_bits = L.kzg_b200_window_bits(handle)
+        self.comb_width = L.kzg_b200_comb_width(handle)
+        self.table_bytes = L.kzg_b200_table_bytes(handle)
+        self.chunk_blobs = L.kzg_b200_chunk_blobs(handle)
 
     @classmethod
-    def load_trusted_setup(cls, g1_bytes, g2_bytes, device=0, window_bits=0):
+    def load_trusted_setup(cls, g1_bytes, g2_bytes, device=0, comb_width=0):
         """reference src/kzg.rs:45-79.  g1_bytes / g2_bytes: lists of 48 / 96 byte strings."""
         g1 = b"".join(bytes(x) for x in g1_bytes) if not isinstance(g1_bytes, (bytes, bytearray)) else bytes(g1_bytes)
         g2 = b"".join(bytes(x) for x in g2_bytes) if not isinstance(g2_bytes, (bytes, bytearray)) else bytes(g2_bytes)
@@ -205,18 +212,18 @@ class KzgSettings:
         h = ctypes.c_void_p()
         b1 = ctypes.create_string_buffer(g1, len(g1))
         b2 = ctypes.create_string_buffer(g2, len(g2))
-        rc = L.kzg_b200_ctx_create(ctypes.addressof(b1), n1, ctypes.addressof(b2), n2, device, window_bits,
+        rc = L.kzg_b200_ctx_create(ctypes.addressof(b1), n1, ctypes.addressof(b2), n2, device, comb_width,
                                    ctypes.byref(h))
         if rc:
             _raise(rc, "load_trusted_setup")
         return cls(h)
 
     @classmethod
-    def load_trusted_setup_file(cls, path, device=0, window_bits=0):
+    def load_trusted_setup_file(cls, path, device=0, comb_width=0):
         """reference src/kzg.rs:906-979."""
         L = load_library()
         h = ctypes.c_void_p()
-        rc = L.kzg_b200_ctx_create_from_file(os.fsencode(path), device, window_bits, ctypes.byref(h))
+        rc = L.kzg_b200_ctx_create_from_file(os.fsencode(path), device, comb_width, ctypes.byref(h))
         if rc:
             _raise(rc, "load_trusted_setup_file")
         return cls(h)
@@ -241,12 +248,12 @@ class Kzg:
     """reference `pub struct Kzg` (src/kzg.rs:983-1079)."""
 
     @staticmethod
-    def load_trusted_setup_file(path, device=0, window_bits=0):
-        return KzgSettings.load_trusted_setup_file(path, device, window_bits)
+    def load_trusted_setup_file(path, device=0, comb_width=0):
+        return KzgSettings.load_trusted_setup_file(path, device, comb_width)
 
     @staticmethod
-    def load_trusted_setup(g1_bytes, g2_bytes, device=0, window_bits=0):
-        return KzgSettings.load_trusted_setup(g1_bytes, g2_bytes, device, window_bits)
+    def load_trusted_setup(g1_bytes, g2_bytes, device=0, comb_width=0):
+        return KzgSettings.load_trusted_setup(g1_bytes, g2_bytes, device, comb_width)
 
     # ---- batched entry points (new): contiguous buffers in, numpy arrays out
     @staticmethod
@@ -316,22 +323,31 @@ class Kzg:
 
     # ---- the reference's single-blob API (src/kzg.rs:1013-1078)
     @staticmethod
+    def _one(buf, size):
+        """A single fixed-size record (the reference's typed `Blob` / `Bytes32` / `Bytes48` make any other length
+        impossible; raw buffers get the same check here instead of being read as a batch)."""
+        b = _raw(buf)
+        if len(b) != size:
+            raise InvalidBytesLength("Invalid byte length. Expected %d got %d" % (size, len(b)))
+        return b
+
+    @staticmethod
     def blob_to_kzg_commitment(blob, s):
-        out, status = Kzg.blob_to_kzg_commitment_batch(_raw(blob), s)
+        out, status = Kzg.blob_to_kzg_commitment_batch(Kzg._one(blob, s.bytes_per_blob), s)
         if status[0]:
             _raise(int(status[0]), "blob_to_kzg_commitment")
         return KzgCommitment(out[0].tobytes())
 
     @staticmethod
     def compute_kzg_proof(blob, z_bytes, s):
-        proofs, ys, status = Kzg.compute_kzg_proof_batch(_raw(blob), _raw(z_bytes), s)
+        proofs, ys, status = Kzg.compute_kzg_proof_batch(Kzg._one(blob, s.bytes_per_blob), Kzg._one(z_bytes, 32), s)
         if status[0]:
             _raise(int(status[0]), "compute_kzg_proof")
         return KzgProof(proofs[0].tobytes()), Bytes32(ys[0].tobytes())
 
     @staticmethod
     def compute_blob_kzg_proof(blob, commitment_bytes, s):
-        out, status = Kzg.compute_blob_kzg_proof_batch(_raw(blob), _raw(commitment_bytes), s)
+        out, status = Kzg.compute_blob_kzg_proof_batch(Kzg._one(blob, s.bytes_per_blob), Kzg._one(commitment_bytes, 48), s)
         if status[0]:
             _raise(int(status[0]), "compute_blob_kzg_proof")
         return KzgProof(out[0].tobytes())
@@ -353,7 +369,8 @@ class Kzg:
 
     @staticmethod
     def verify_blob_kzg_proof(blob, commitment_bytes, proof_bytes, s):
-        return Kzg.verify_blob_kzg_proof_batch_raw(_raw(blob), _raw(commitment_bytes), _raw(proof_bytes), 1, s)
+        return Kzg.verify_blob_kzg_proof_batch_raw(Kzg._one(blob, s.bytes_per_blob), Kzg._one(commitment_bytes, 48),
+                                                   Kzg._one(proof_bytes, 48), 1, s)
 
     @staticmethod
     def verify_blob_kzg_proof_batch(blobs, commitments, proofs, s):

@@ -22,14 +22,32 @@ def minimal_setup_bytes():
     return raw[:4 * 48], raw[4 * 48:]
 
 
+# The reference's vectors run twice: on a small comb (6 MB of table) and on the configuration bench.py measures
+# (comb_width 0 = automatic: 23 on an empty B200, 72 GB of table, 4096-blob chunks).
+VECTOR_WIDTHS = [8, 0]
+VECTOR_WIDTH_IDS = ["g8", "auto"]
+
+
 @functools.lru_cache(maxsize=None)
-def gpu_settings(preset="mainnet", window_bits=8):
+def gpu_settings(preset="mainnet", comb_width=8):
+    """One context per (preset, comb width), kept for the whole test session.  Explicit widths get a small
+    workspace (128-blob chunks) so that several contexts fit beside the automatic one."""
     from kzg_rust_b200 import KzgSettings
-    if preset == "mainnet":
-        g = golden()
-        return KzgSettings.load_trusted_setup(g.g1_bytes, g.g2_bytes, 0, window_bits)
-    g1, g2 = minimal_setup_bytes()
-    return KzgSettings.load_trusted_setup(g1, g2, 0, window_bits)
+    old = os.environ.get("KZG_B200_CHUNK")
+    if comb_width != 0:
+        os.environ["KZG_B200_CHUNK"] = "128"
+    try:
+        if preset == "mainnet":
+            g = golden()
+            return KzgSettings.load_trusted_setup(g.g1_bytes, g.g2_bytes, 0, comb_width)
+        g1, g2 = minimal_setup_bytes()
+        return KzgSettings.load_trusted_setup(g1, g2, 0, comb_width)
+    finally:
+        if comb_width != 0:
+            if old is None:
+                del os.environ["KZG_B200_CHUNK"]
+            else:
+                os.environ["KZG_B200_CHUNK"] = old
 
 
 @functools.lru_cache(maxsize=None)

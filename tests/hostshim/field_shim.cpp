@@ -1,7 +1,7 @@
 // Host-side shim exposing the product's field templates (host code path of
 // kzg_rust_b200/csrc/bigint.cuh) to ctypes, so tests can compare them with Python ints.
 #include "../../kzg_rust_b200/csrc/fields.cuh"
-#include "../../kzg_rust_b200/csrc/fp_hybrid.cuh"
+#include "../../tools/experiments/fp_hybrid.cuh"
 using namespace kzg;
 extern "C" {
 void shim_fp_mul(const uint32_t *a, const uint32_t *b, uint32_t *r) { fp_t x, y, z; memcpy(x.l, a, 48); memcpy(y.l, b, 48); fe_mul(z, x, y); memcpy(r, z.l, 48); }

@@ -1,7 +1,8 @@
 // CPU walk-through of the product's commitment pipeline (host code path of the same
-// headers the CUDA kernels are built from): decode setup -> bit-reverse -> window bases
-// -> table levels -> digits -> gather level -> tree levels -> compress.  "Threads" are
-// iterated sequentially.  Small presets only (n = 4); used by tests/test_host_logic.py.
+// headers the CUDA kernels are built from): decode setup -> bit-reverse -> comb table levels
+// -> sign words -> comb digits -> gather level -> tree levels -> Horner -> compress.  "Threads" are
+// iterated sequentially.  Small point counts only; used by tests/test_host_logic.py.
+#include <cstring>
 #include <vector>
 #include "../../kzg_rust_b200/csrc/msm.cuh"
 #include "../../kzg_rust_b200/csrc/blobpath.cuh"
@@ -14,71 +15,116 @@ static void run_level(const Policy &pol, uint64_t total, int T, int k) {
 }
 static uint32_t bitrev(uint32_t v, int n) { uint32_t r = 0; for (int o = n; o > 1; o >>= 1) { r = (r << 1) | (v & 1); v >>= 1; } return r; }
 
-static int build_table(std::vector<g1_affine_t> &table, const uint8_t *g1_bytes, int n, int c, int T, int k) {
-    const uint32_t D = 1u << (c - 1);
-    table.resize((size_t)n * D);
-    for (int i = 0; i < n; i++) {
-        g1_affine_t p;
-        if (g1_decode_thread(p, g1_bytes + 48 * bitrev(i, n), false)) return KZG_BADARGS;
-        table[(size_t)i * D] = p;
+struct Comb {
+    int n, g, G, n_pad;
+    uint64_t E;
+    std::vector<g1_affine_t> bases, table;
+};
+// bitrev_order = 0 keeps the points in the order given (n need not be a power of two then)
+static int build_comb(Comb &cb, const uint8_t *g1_bytes, int n, int g, int T, int k, int bitrev_order) {
+    if (g > n) g = n;
+    cb.n = n; cb.g = g; cb.G = (n + g - 1) / g; cb.n_pad = cb.G * g; cb.E = 1ull << (g - 1);
+    cb.bases.resize(cb.n_pad);
+    for (int i = 0; i < cb.n_pad; i++) {
+        if (i < n) {
+            if (g1_decode_thread(cb.bases[i], g1_bytes + 48 * (bitrev_order ? bitrev(i, n) : (uint32_t)i), false)) return KZG_BADARGS;
+        } else {
+            g1a_set_inf(cb.bases[i]);
+        }
     }
-    for (int L = 0; L + 1 < c; L++) {
-        TableLevelPolicy pol{table.data(), D, (uint32_t)L};
-        run_level(pol, (uint64_t)n << L, T, k);
+    cb.table.resize((size_t)cb.G * cb.E);
+    for (int q = 0; q < cb.G; q++) cb.table[(size_t)q << (g - 1)] = cb.bases[(size_t)q * g];
+    for (int m = 1; m < g; m++) {
+        const uint64_t total = (uint64_t)cb.G << (m - 1);
+        run_level(CombLevelPolicy{cb.table.data(), cb.bases.data(), (uint32_t)g, (uint32_t)m, 1u}, total, T, k);
+        run_level(CombLevelPolicy{cb.table.data(), cb.bases.data(), (uint32_t)g, (uint32_t)m, 0u}, total, T, k);
     }
     return 0;
 }
-
-extern "C" int shim_commit(const uint8_t *g1_bytes, int n, int c, const uint8_t *blobs, int B, uint8_t *out,
-                           int *status, int T, int k) {
-    const int W = msm_num_windows(c);
-    const uint32_t D = 1u << (c - 1);
-    std::vector<g1_affine_t> table;
-    if (build_table(table, g1_bytes, n, c, T, k)) return KZG_BADARGS;
-    std::vector<int32_t> digits((size_t)B * W * n);
-    for (int b = 0; b < B; b++) status[b] = 0;
-    for (uint64_t e = 0; e < (uint64_t)B * n; e++) blob_digits_thread(blobs, e, n, c, W, digits.data(), status);
-    // point-major copy of the digits (k_transpose_digits on the device)
-    std::vector<int32_t> digits_t((size_t)B * W * n);
+// sums over the comb of B scalar vectors given as sign words [b][8][n_pad] -> compressed points
+static void comb_msm(const Comb &cb, const std::vector<uint32_t> &sw, int B, uint8_t *out, int T, int k) {
+    const int W = KZG_COMB_WINDOWS;
+    std::vector<uint32_t> digits((size_t)cb.G * W * B);
     for (int b = 0; b < B; b++)
-        for (int j = 0; j < W; j++)
-            for (int i = 0; i < n; i++) digits_t[((size_t)i * W + j) * B + b] = digits[((size_t)b * W + j) * n + i];
+        for (int q = 0; q < cb.G; q++) comb_index_thread(sw.data(), (uint32_t)b, (uint32_t)q, cb.g, cb.n_pad, (uint32_t)B, digits.data());
     const uint64_t R = (uint64_t)B * W;
     const FastDiv fd = FastDiv::make((uint32_t)R);
-    uint32_t rows = n / 2;
-    std::vector<g1_affine_t> a((size_t)R * rows), b2((size_t)R * rows);
-    GatherPolicy gp{table.data(), digits_t.data(), a.data(), fd, D};
-    run_level(gp, R * rows, T, k);
+    uint32_t rows = (uint32_t)cb.G;
+    std::vector<g1_affine_t> a((size_t)R * ((rows + 1) / 2)), b2((size_t)R * ((rows + 1) / 2));
+    if (rows / 2) run_level(GatherPolicy{cb.table.data(), digits.data(), a.data(), fd, (uint32_t)cb.E}, R * (rows / 2), T, k);
+    if (rows & 1) {  // k_gather_copy on the device
+        for (uint64_t r = 0; r < R; r++) {
+            uint32_t d = digits[(uint64_t)(rows - 1) * R + r];
+            g1_affine_t p = cb.table[(uint64_t)(rows - 1) * cb.E + (d & 0x7fffffffu)];
+            if ((d >> 31) && !g1a_is_inf(p)) fe_neg_lazy(p.y, p.y);
+            a[(uint64_t)(rows / 2) * R + r] = p;
+        }
+    }
+    rows = (rows + 1) / 2;
     g1_affine_t *in = a.data(), *o = b2.data();
     while (rows > 1) {
-        rows /= 2;
-        PairPolicy tp{in, o, fd};
-        run_level(tp, R * rows, T, k);
+        run_level(PairPolicy{in, o, fd}, R * (rows / 2), T, k);
+        if (rows & 1) memcpy(o + (uint64_t)(rows / 2) * R, in + (uint64_t)(rows - 1) * R, R * sizeof(g1_affine_t));
+        rows = (rows + 1) / 2;
         std::swap(in, o);
     }
     for (int b = 0; b < B; b++) {
         g1_affine_t p;
-        horner_thread(p, in + b, (size_t)B, c, W);
+        horner_thread(p, in + b, (size_t)B, 1, W);
         g1a_compress(out + 48 * b, p);
+    }
+}
+
+// commitments of B blobs of n elements (n a power of two: the setup is bit-reversal permuted like src/kzg.rs:895-896)
+extern "C" int shim_commit(const uint8_t *g1_bytes, int n, int g, const uint8_t *blobs, int B, uint8_t *out,
+                           int *status, int T, int k) {
+    Comb cb;
+    if (build_comb(cb, g1_bytes, n, g, T, k, 1)) return KZG_BADARGS;
+    std::vector<uint32_t> sw((size_t)B * 8 * cb.n_pad);
+    for (int b = 0; b < B; b++) status[b] = 0;
+    for (uint64_t e = 0; e < (uint64_t)B * cb.n_pad; e++) blob_sign_words_thread(blobs, e, n, cb.n_pad, sw.data(), status);
+    comb_msm(cb, sw, B, out, T, k);
+    return 0;
+}
+// the same MSM over ANY number of points in the order given, scalars as canonical limbs [b][n][8], against the plain
+// ladder: out_comb / out_ladder = sum_i s_i P_i compressed (odd group counts, padding and every comb width get exercised)
+extern "C" int shim_msm_vs_ladder(const uint8_t *g1_bytes, int n, int g, const uint32_t *scalars, int B, uint8_t *out_comb,
+                                  uint8_t *out_ladder, int T, int k) {
+    Comb cb;
+    if (build_comb(cb, g1_bytes, n, g, T, k, 0)) return KZG_BADARGS;
+    std::vector<uint32_t> sw((size_t)B * 8 * cb.n_pad);
+    for (uint64_t e = 0; e < (uint64_t)B * cb.n_pad; e++)
+        fr_sign_words_thread(reinterpret_cast<const fr_t *>(scalars), e, n, cb.n_pad, sw.data());
+    comb_msm(cb, sw, B, out_comb, T, k);
+    for (int b = 0; b < B; b++) {
+        g1_jac_t acc;
+        g1j_set_inf(acc);
+        for (int i = 0; i < n; i++) {
+            g1_jac_t t;
+            g1j_mul(t, cb.bases[i], scalars + ((size_t)b * n + i) * 8, 255);
+            g1j_add(acc, acc, t);
+        }
+        g1_affine_t p;
+        g1j_to_affine(p, acc);
+        g1a_compress(out_ladder + 48 * b, p);
     }
     return 0;
 }
-
 // The precomputed table alone (same layout as the device table), for debugging / tests.
-extern "C" int shim_table(const uint8_t *g1_bytes, int n, int c, g1_affine_t *table_out, int T, int k) {
-    std::vector<g1_affine_t> table;
-    if (build_table(table, g1_bytes, n, c, T, k)) return KZG_BADARGS;
-    memcpy(table_out, table.data(), table.size() * sizeof(g1_affine_t));
+extern "C" int shim_table(const uint8_t *g1_bytes, int n, int g, g1_affine_t *table_out, int T, int k) {
+    Comb cb;
+    if (build_comb(cb, g1_bytes, n, g, T, k, 1)) return KZG_BADARGS;
+    memcpy(table_out, cb.table.data(), cb.table.size() * sizeof(g1_affine_t));
     return 0;
 }
-// signed-digit recoding of one canonical scalar (8 little-endian words) for a given window
-extern "C" int shim_recode(const uint32_t *scalar, int c, int32_t *digits_out) {
+// the 255 signs of one canonical scalar (8 little-endian words in, 8 words out)
+extern "C" void shim_sign_words(const uint32_t *scalar, uint32_t *out) {
     fr_t s;
     memcpy(s.l, scalar, 32);
-    int W = msm_num_windows(c);
-    recode_signed(s, c, W, digits_out, 1);
-    return W;
+    scalar_sign_words(out, s);
 }
+extern "C" uint32_t shim_comb_digit(uint32_t pattern, int g) { return comb_digit(pattern, g); }
+extern "C" void shim_transpose32(uint32_t *a) { transpose32(a); }
 // [k]P by the plain ladder and by the GLV ladder (g1.cuh), both compressed; k = 8 little-endian words
 extern "C" int shim_g1_mul_both(const uint8_t *point48, const uint32_t *k, uint8_t *out_plain, uint8_t *out_glv, uint32_t *k1k2) {
     g1_affine_t p;

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from golden_util import golden
-from gpu_util import gpu_settings, oracle_settings, synthetic_blobs
+from gpu_util import VECTOR_WIDTH_IDS, VECTOR_WIDTHS, gpu_settings, oracle_settings, synthetic_blobs
 
 pytestmark = pytest.mark.gpu
 G = golden()
@@ -18,11 +18,12 @@ def _kzg():
     return kzg_rust_b200
 
 
+@pytest.mark.parametrize("width", VECTOR_WIDTHS, ids=VECTOR_WIDTH_IDS)
 @pytest.mark.parametrize("case", G.by_fn("blob_to_kzg_commitment"), ids=[c["name"] for c in G.by_fn("blob_to_kzg_commitment")])
-def test_reference_vectors(case):
+def test_reference_vectors(case, width):
     """reference src/lib.rs:30-52."""
     k = _kzg()
-    s = gpu_settings("mainnet", 8)
+    s = gpu_settings("mainnet", width)
     try:
         blob = k.Blob.from_bytes(G.get_bytes(case["input"]["blob"]))
     except (k.Error, ValueError):
@@ -36,10 +37,11 @@ def test_reference_vectors(case):
     assert "0x" + out.to_bytes().hex() == case["output"]
 
 
-def test_vectors_as_one_batch():
+@pytest.mark.parametrize("width", VECTOR_WIDTHS, ids=VECTOR_WIDTH_IDS)
+def test_vectors_as_one_batch(width):
     """All well-sized vector blobs in one batched call: per-blob status, no cross-talk."""
     k = _kzg()
-    s = gpu_settings("mainnet", 8)
+    s = gpu_settings("mainnet", width)
     cases = [c for c in G.by_fn("blob_to_kzg_commitment") if len(G.get_bytes(c["input"]["blob"])) == 131072]
     blobs = b"".join(G.get_bytes(c["input"]["blob"]) for c in cases)
     out, status = k.Kzg.blob_to_kzg_commitment_batch(blobs, s)
@@ -50,11 +52,11 @@ def test_vectors_as_one_batch():
             assert status[i] == 0 and "0x" + out[i].tobytes().hex() == c["output"]
 
 
-@pytest.mark.parametrize("window_bits", [5, 8, 11])
-def test_random_blobs_vs_oracle(window_bits):
+@pytest.mark.parametrize("comb_width", [5, 8, 11])
+def test_random_blobs_vs_oracle(comb_width):
     k = _kzg()
-    s = gpu_settings("mainnet", window_bits)
-    blobs = synthetic_blobs(24, seed=0xB200 + window_bits)
+    s = gpu_settings("mainnet", comb_width)
+    blobs = synthetic_blobs(24, seed=0xB200 + comb_width)
     # sprinkle edge values: 0, 1, r-1 and a duplicate blob
     blobs[1, :32] = 0
     blobs[2, 32:64] = np.frombuffer((R - 1).to_bytes(32, "big"), dtype=np.uint8)
@@ -109,25 +111,101 @@ def test_large_batch_spans_chunks():
     s.close()
 
 
-def test_work_pulling_kernel_vs_oracle():
-    """KZG_B200_DYNAMIC=1: the MSM levels run batch_add_dyn_kernel (warps pull 32-addition tiles from a
-    counter, per-warp inversion).  Same bytes as the oracle, special cases included, several chunks."""
+@pytest.mark.parametrize("env", [{"KZG_B200_ADD_BLOCKS": "2"}, {"KZG_B200_ADD_BLOCKS": "4"}, {"KZG_B200_BATCH_K": "3"},
+                                 {"KZG_B200_LANES": "1", "KZG_B200_GRID_BLOCKS": "1"}],
+                         ids=["2-blocks-per-sm", "4-blocks-per-sm", "short-batches", "one-lane"])
+def test_kernel_configurations_vs_oracle(env):
+    """The launch shapes of the addition kernel (register budget, batch length, lanes) are knobs: same bytes as the
+    oracle for each, special cases included, several chunks."""
     k = _kzg()
-    os.environ["KZG_B200_DYNAMIC"] = "1"
-    os.environ["KZG_B200_CHUNK"] = "40"
+    env = dict(env, KZG_B200_CHUNK="40")
+    os.environ.update(env)
     try:
         g = golden()
         s = k.KzgSettings.load_trusted_setup(g.g1_bytes, g.g2_bytes, 0, 9)
     finally:
-        del os.environ["KZG_B200_DYNAMIC"]
-        del os.environ["KZG_B200_CHUNK"]
+        for key in env:
+            del os.environ[key]
     blobs = synthetic_blobs(100, seed=0xD1)
-    blobs[3, :] = 0                      # every addition meets infinity
+    blobs[3, :] = 0                      # every scalar is recoded as r: the sums cancel to infinity
     blobs[4] = 0
-    blobs[4, 31::32] = 1                 # the constant polynomial 1: equal digits everywhere
+    blobs[4, 31::32] = 1                 # the constant polynomial 1: the same table entry in every group
+    blobs[5] = 0
+    blobs[5, 31::32] = 2                 # even scalars: recoded as r - 2 with flipped signs
     blobs[50] = blobs[49]
     out, status = k.Kzg.blob_to_kzg_commitment_batch(blobs, s)
     assert not status.any()
     exp, est = oracle_settings("mainnet").blob_to_kzg_commitment_many(blobs, nthreads=os.cpu_count() or 1)
     assert not est.any() and np.array_equal(out, exp)
     s.close()
+
+
+def test_load_trusted_setup_file(tmp_path):
+    """reference load_trusted_setup_file (src/kzg.rs:906-979): the text layout of trusted_setup.txt through
+    kzg_b200_ctx_create_from_file, then one vector; malformed files are rejected with the reference's error kinds."""
+    k = _kzg()
+    path = tmp_path / "trusted_setup.txt"
+    G.write_setup_text(str(path))
+    s = k.Kzg.load_trusted_setup_file(str(path), 0, 6)
+    assert s.field_elements_per_blob == 4096 and s.comb_width == 6
+    case = next(c for c in G.by_fn("blob_to_kzg_commitment") if c["output"] is not None)
+    out = k.Kzg.blob_to_kzg_commitment(k.Blob.from_bytes(G.get_bytes(case["input"]["blob"])), s)
+    assert "0x" + out.to_bytes().hex() == case["output"]
+    s.close()
+    text = path.read_text().split("\n")
+    bad = tmp_path / "bad_count.txt"
+    bad.write_text("\n".join(["4095"] + text[1:]))
+    with pytest.raises(k.InvalidTrustedSetup):
+        k.Kzg.load_trusted_setup_file(str(bad), 0, 6)
+    bad = tmp_path / "bad_hex.txt"
+    bad.write_text("\n".join(text[:2] + ["zz" + text[2][2:]] + text[3:]))
+    with pytest.raises(k.InvalidHexFormat):
+        k.Kzg.load_trusted_setup_file(str(bad), 0, 6)
+    bad = tmp_path / "short.txt"
+    bad.write_text("\n".join(text[:100]))
+    with pytest.raises(k.InvalidTrustedSetup):
+        k.Kzg.load_trusted_setup_file(str(bad), 0, 6)
+    with pytest.raises(k.InvalidTrustedSetup):
+        k.Kzg.load_trusted_setup_file(str(tmp_path / "missing.txt"), 0, 6)
+    bad = tmp_path / "not_a_point.txt"
+    bad.write_text("\n".join(text[:2] + ["8" + "0" * 94 + "05"] + text[3:]))  # x = 5: x^3 + 4 is not a square
+    with pytest.raises(k.Error):
+        k.Kzg.load_trusted_setup_file(str(bad), 0, 6)
+
+
+def test_every_commitment_of_a_large_batch_by_the_tau_identity():
+    """C == [p(tau)] G1 on EVERY blob (the bundled setup is the public testing setup,
+    tau = 1337) at the benchmarked configuration, device-resident, several chunks; a tampered commitment is flagged."""
+    import ctypes
+    import torch
+    k = _kzg()
+    L = k.load_library()
+    s = gpu_settings("mainnet", 0)
+    n = 2 * s.chunk_blobs + 77
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234)
+    blobs = torch.randint(0, 256, (n, 4096, 32), dtype=torch.uint8, device=dev, generator=gen)
+    blobs[:, :, 0] = 0
+    blobs[5] = 0                                     # zero polynomial -> infinity
+    blobs[6] = 0
+    blobs[6, :, 31] = 9                              # constant polynomial
+    out = torch.zeros((n, 48), dtype=torch.uint8, device=dev)
+    st = torch.zeros(n, dtype=torch.int32, device=dev)
+    assert L.kzg_b200_blob_to_kzg_commitment_device(s._h, blobs.data_ptr(), n, out.data_ptr(), st.data_ptr()) == 0
+    assert L.kzg_b200_synchronize(s._h) == 0 and not bool(st.any().item())
+    assert out[5].cpu().numpy().tobytes() == bytes([0xc0]) + bytes(47)
+    ok = torch.zeros(n, dtype=torch.int32, device=dev)
+    tau = (1337).to_bytes(32, "big")
+    assert L.kzg_b200_debug_check_tau_identity(s._h, blobs.data_ptr(), out.data_ptr(), n, tau, ok.data_ptr()) == 0
+    assert int(ok.sum().item()) == n
+    out[n // 2, 47] ^= 1
+    out[3] = out[4]
+    assert L.kzg_b200_debug_check_tau_identity(s._h, blobs.data_ptr(), out.data_ptr(), n, tau, ok.data_ptr()) == 0
+    bad = set(torch.nonzero(ok == 0).flatten().cpu().tolist())
+    assert bad == {3, n // 2}
+    # and the sample the oracle can afford
+    exp, est = oracle_settings("mainnet").blob_to_kzg_commitment_many(blobs[8:8 + 32].reshape(32, -1).cpu().numpy(), nthreads=os.cpu_count() or 1)
+    out[3] = 0
+    got = out[8:8 + 32].cpu().numpy()
+    assert not est.any() and np.array_equal(got, exp)

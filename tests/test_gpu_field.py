@@ -1,6 +1,5 @@
 """-m gpu: the device field arithmetic itself (through kzg_b200_debug_field_op) against Python integers:
-the canonical Montgomery operations, the lazy [0, 2p) forms the MSM levels use, and the two-pipe
-multiplication of csrc/fp_hybrid.cuh (FP64-pipe product + IMAD-pipe reduction) -- all bit-exact."""
+the canonical Montgomery operations and the lazy [0, 2p) forms the MSM levels use -- all bit-exact."""
 import ctypes
 
 import numpy as np
@@ -72,12 +71,3 @@ def test_lazy_fp_ops_stay_below_2p():
     got = _run(8, av, bv, 12)
     assert all(g < 2 * P for g in got)
     assert [g % P for g in got] == [(x - y) % P for x, y in zip(av, bv)]
-
-
-def test_two_pipe_multiplication_equals_fe_mul():
-    Rp_inv = pow(pow(2, 384, P), -1, P)
-    av, bv = _values(P, P, 6000, 4)
-    exp = [x * y * Rp_inv % P for x, y in zip(av, bv)]
-    assert _run(5, av, bv, 12) == exp
-    assert _run(0, av, bv, 12) == exp
-    assert _run(6, av, av, 12) == [x * x * Rp_inv % P for x in av]

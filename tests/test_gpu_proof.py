@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from golden_util import golden
-from gpu_util import gpu_settings, oracle_settings, synthetic_blobs
+from gpu_util import VECTOR_WIDTH_IDS, VECTOR_WIDTHS, gpu_settings, oracle_settings, synthetic_blobs
 
 pytestmark = pytest.mark.gpu
 G = golden()
@@ -23,11 +23,12 @@ def _ids(fn):
     return [c["name"] for c in G.by_fn(fn)]
 
 
+@pytest.mark.parametrize("width", VECTOR_WIDTHS, ids=VECTOR_WIDTH_IDS)
 @pytest.mark.parametrize("case", G.by_fn("compute_kzg_proof"), ids=_ids("compute_kzg_proof"))
-def test_compute_kzg_proof_vectors(case):
+def test_compute_kzg_proof_vectors(case, width):
     """reference src/lib.rs:54-79 (36 valid cases, 18 of them with z inside the domain)."""
     k = _kzg()
-    s = gpu_settings("mainnet", 8)
+    s = gpu_settings("mainnet", width)
     try:
         blob = k.Blob.from_bytes(G.get_bytes(case["input"]["blob"]))
         z = k.Bytes32.from_bytes(G.get_bytes(case["input"]["z"]))
@@ -42,11 +43,12 @@ def test_compute_kzg_proof_vectors(case):
     assert ["0x" + proof.to_bytes().hex(), "0x" + y.to_bytes().hex()] == case["output"]
 
 
+@pytest.mark.parametrize("width", VECTOR_WIDTHS, ids=VECTOR_WIDTH_IDS)
 @pytest.mark.parametrize("case", G.by_fn("compute_blob_kzg_proof"), ids=_ids("compute_blob_kzg_proof"))
-def test_compute_blob_kzg_proof_vectors(case):
+def test_compute_blob_kzg_proof_vectors(case, width):
     """reference src/lib.rs:81-105."""
     k = _kzg()
-    s = gpu_settings("mainnet", 8)
+    s = gpu_settings("mainnet", width)
     try:
         blob = k.Blob.from_bytes(G.get_bytes(case["input"]["blob"]))
         c = k.Bytes48.from_bytes(G.get_bytes(case["input"]["commitment"]))
@@ -61,10 +63,11 @@ def test_compute_blob_kzg_proof_vectors(case):
     assert "0x" + proof.to_bytes().hex() == case["output"]
 
 
-def test_proof_vectors_as_one_batch():
+@pytest.mark.parametrize("width", VECTOR_WIDTHS, ids=VECTOR_WIDTH_IDS)
+def test_proof_vectors_as_one_batch(width):
     """All well-formed compute_blob_kzg_proof vectors in one batched call: per-blob status."""
     k = _kzg()
-    s = gpu_settings("mainnet", 8)
+    s = gpu_settings("mainnet", width)
     cases = [c for c in G.by_fn("compute_blob_kzg_proof")
              if len(G.get_bytes(c["input"]["blob"])) == 131072 and len(G.get_bytes(c["input"]["commitment"])) == 48]
     blobs = b"".join(G.get_bytes(c["input"]["blob"]) for c in cases)
@@ -77,12 +80,12 @@ def test_proof_vectors_as_one_batch():
             assert status[i] == 0 and "0x" + out[i].tobytes().hex() == c["output"], c["name"]
 
 
-@pytest.mark.parametrize("window_bits", [6, 9])
-def test_config2_64_blob_batch_vs_oracle(window_bits):
+@pytest.mark.parametrize("comb_width", [6, 9, 0])
+def test_config2_64_blob_batch_vs_oracle(comb_width):
     """BASELINE.json config 2: compute_blob_kzg_proof on a 64-blob synthetic batch, byte-equal
     with the CPU restatement, then verified as a batch (and rejected after one proof is swapped)."""
     k = _kzg()
-    s = gpu_settings("mainnet", window_bits)
+    s = gpu_settings("mainnet", comb_width)
     o = oracle_settings("mainnet")
     blobs = synthetic_blobs(64, seed=0xB200)
     blobs[5, :] = 0                                           # zero polynomial: commitment and proof at infinity

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from golden_util import golden
-from gpu_util import gpu_settings, oracle_settings, synthetic_blobs
+from gpu_util import VECTOR_WIDTH_IDS, VECTOR_WIDTHS, gpu_settings, oracle_settings, synthetic_blobs
 
 pytestmark = pytest.mark.gpu
 G = golden()
@@ -22,11 +22,12 @@ def _ids(fn):
     return [c["name"] for c in G.by_fn(fn)]
 
 
+@pytest.mark.parametrize("width", VECTOR_WIDTHS, ids=VECTOR_WIDTH_IDS)
 @pytest.mark.parametrize("case", G.by_fn("verify_blob_kzg_proof"), ids=_ids("verify_blob_kzg_proof"))
-def test_verify_blob_kzg_proof_vectors(case):
+def test_verify_blob_kzg_proof_vectors(case, width):
     """reference src/lib.rs:142-175."""
     k = _kzg()
-    s = gpu_settings("mainnet", 8)
+    s = gpu_settings("mainnet", width)
     try:
         blob = k.Blob.from_bytes(G.get_bytes(case["input"]["blob"]))
         c = k.Bytes48.from_bytes(G.get_bytes(case["input"]["commitment"]))
@@ -42,11 +43,12 @@ def test_verify_blob_kzg_proof_vectors(case):
     assert ok is case["output"]
 
 
+@pytest.mark.parametrize("width", VECTOR_WIDTHS, ids=VECTOR_WIDTH_IDS)
 @pytest.mark.parametrize("case", G.by_fn("verify_blob_kzg_proof_batch"), ids=_ids("verify_blob_kzg_proof_batch"))
-def test_verify_blob_kzg_proof_batch_vectors(case):
+def test_verify_blob_kzg_proof_batch_vectors(case, width):
     """reference src/lib.rs:177-203."""
     k = _kzg()
-    s = gpu_settings("mainnet", 8)
+    s = gpu_settings("mainnet", width)
     try:
         blobs = [k.Blob.from_bytes(G.get_bytes(v)) for v in case["input"]["blobs"]]
         cs = [k.Bytes48.from_bytes(G.get_bytes(v)) for v in case["input"]["commitments"]]
@@ -152,7 +154,7 @@ def test_pairing_check_matches_oracle():
 
 def test_config5_size_16384_blobs_round_trip_properties():
     """BASELINE.json configs[3..4] size on one GPU, checked through size-independent properties: 16,384
-    synthetic blobs are committed and proved on the device (default window width, several chunks, both
+    synthetic blobs are committed and proved on the device (default comb width, several chunks, both
     lanes), then (1) the whole batch verifies -- one pairing equation over all 16,384 (C_i, proof_i), which
     holds only if every proof opens its commitment at its own challenge, (2) the same batch with two proofs
     swapped is rejected, (3) repeated blobs give repeated commitments and proofs wherever they sit in the
@@ -161,7 +163,7 @@ def test_config5_size_16384_blobs_round_trip_properties():
     import torch
     import kzg_rust_b200 as k
     L = k.load_library()
-    s = k.KzgSettings.load_trusted_setup(G.g1_bytes, G.g2_bytes, 0, 0)
+    s = gpu_settings("mainnet", 0)
     n = 16384
     dev = torch.device("cuda", 0)
     gen = torch.Generator(device=dev)
@@ -194,16 +196,16 @@ def test_config5_size_16384_blobs_round_trip_properties():
     assert not est.any() and np.array_equal(cms[idx], exp_c)
     exp_p, est = o.compute_blob_kzg_proof_many(blobs[idx], exp_c, nthreads=os.cpu_count() or 1)
     assert not est.any() and np.array_equal(prs[idx], exp_p)
-    s.close()
 
 
+@pytest.mark.parametrize("width", VECTOR_WIDTHS, ids=VECTOR_WIDTH_IDS)
 @pytest.mark.parametrize("case", G.by_fn("verify_kzg_proof"), ids=_ids("verify_kzg_proof"))
-def test_verify_kzg_proof_vectors(case):
+def test_verify_kzg_proof_vectors(case, width):
     """reference src/lib.rs:112-140: all 92 vectors (correct / incorrect proofs, points at infinity, z in and
     out of the domain, non-canonical z / y, commitments and proofs off the curve or outside G1) through
     kzg_b200_verify_kzg_proof -- phase B of the batch path with one term and the points subgroup-checked."""
     k = _kzg()
-    s = gpu_settings("mainnet", 8)
+    s = gpu_settings("mainnet", width)
     try:
         c = k.Bytes48.from_bytes(G.get_bytes(case["input"]["commitment"]))
         z = k.Bytes32.from_bytes(G.get_bytes(case["input"]["z"]))

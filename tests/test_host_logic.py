@@ -2,9 +2,9 @@
 the CUDA kernels are built from), the host-side pairing, and the C-ABI surface.
 
   * field arithmetic of kzg_rust_b200/csrc/bigint.cuh vs Python integers
-  * the whole commitment pipeline (table -> digits -> gather level -> tree levels -> Horner ->
+  * the whole commitment pipeline (comb table -> digits -> gather level -> tree levels -> Horner ->
     compress) walked thread by thread on the CPU for the n = 4 preset, vs the oracle
-  * signed-digit recoding invariants for every window width
+  * the signed comb recoding (sign words, bit transpose, table index) and the comb MSM vs a plain ladder
   * libkzg_b200.so loads and exports every symbol include/kzg_b200.h declares
   * the host pairing (stand-in for blst's) vs the oracle's
 """
@@ -98,31 +98,52 @@ def test_fp_and_fr_arithmetic_vs_python(field):
     assert not field.shim_fr_canonical(_limbs(2 ** 256 - 1, 8))
 
 
-@pytest.mark.parametrize("c", list(range(2, 21)))
-def test_signed_digit_recoding(msm, c):
-    rng = np.random.default_rng(c)
-    vals = [0, 1, R - 1, R - 2, 2 ** 254, 2 ** 248 - 1] + [int.from_bytes(rng.bytes(32), "big") % R for _ in range(50)]
-    digs = (ctypes.c_int32 * 130)()
+def test_sign_word_recoding(msm):
+    """Every scalar as sum_j (+-1) 2^j mod r (blobpath.cuh scalar_sign_words): the 255 signs reproduce it."""
+    rng = np.random.default_rng(3)
+    vals = [0, 1, 2, 3, R - 1, R - 2, 2 ** 254, 2 ** 254 + 1, 2 ** 248 - 1, (R - 1) // 2, (R + 1) // 2]
+    vals += [int.from_bytes(rng.bytes(32), "big") % R for _ in range(200)]
+    out = (ctypes.c_uint32 * 8)()
     for v in vals:
-        W = msm.shim_recode(_limbs(v, 8), c, digs)
-        assert W * c >= 255
-        assert all(abs(digs[j]) <= 1 << (c - 1) for j in range(W))
-        assert sum(digs[j] << (c * j) for j in range(W)) == v
+        msm.shim_sign_words(_limbs(v, 8), out)
+        bits = _val(out)
+        assert bits >> 255 == 0
+        signed = sum((1 if (bits >> j) & 1 else -1) << j for j in range(255))
+        assert signed % R == v, v
+        assert signed in (v, v - R)
 
 
-@pytest.mark.parametrize("c,T,k", [(2, 4, 3), (5, 8, 4), (6, 32, 1), (9, 16, 64)])
-def test_commit_pipeline_on_cpu_minimal_preset(msm, c, T, k):
+def test_bit_transpose_and_comb_digit(msm):
+    rng = np.random.default_rng(4)
+    a = [int(x) for x in rng.integers(0, 2 ** 32, size=32, dtype=np.uint64)]
+    arr = (ctypes.c_uint32 * 32)(*a)
+    msm.shim_transpose32(arr)
+    for i in range(32):
+        for j in range(32):
+            assert (arr[i] >> j) & 1 == (a[j] >> i) & 1
+    msm.shim_comb_digit.restype = ctypes.c_uint32
+    for g in (1, 2, 5, 23, 24):
+        for _ in range(50):
+            pat = int(rng.integers(0, 2 ** g))
+            d = msm.shim_comb_digit(pat, g)
+            neg, idx = d >> 31, d & 0x7fffffff
+            full = pat if not neg else (~pat) & ((1 << g) - 1)
+            assert full & 1 == 1 and idx == full >> 1 and neg == (1 - (pat & 1))
+
+
+@pytest.mark.parametrize("g,T,k", [(1, 4, 3), (2, 8, 4), (3, 32, 1), (4, 16, 64), (9, 4, 2)])
+def test_commit_pipeline_on_cpu_minimal_preset(msm, g, T, k):
     """The product's own pipeline, thread by thread on the CPU, for kzg_minimal."""
     g1, _ = minimal_setup_bytes()
     o = oracle_settings("minimal")
-    rng = np.random.default_rng(100 + c)
-    rows = [[0, 0, 0, 0], [R - 1] * 4, [1, 0, 0, 0], [0, 0, 5, 0], [7, 7, 7, 7], [R, 0, 0, 0]]
-    rows += [[int.from_bytes(rng.bytes(32), "big") % R for _ in range(4)] for _ in range(10)]
+    rng = np.random.default_rng(100 + g)
+    rows = [[0, 0, 0, 0], [R - 1] * 4, [1, 0, 0, 0], [0, 0, 5, 0], [7, 7, 7, 7], [R, 0, 0, 0], [2, 2, 2, 2]]
+    rows += [[int.from_bytes(rng.bytes(32), "big") % R for _ in range(4)] for _ in range(5)]
     blobs = b"".join(b"".join(v.to_bytes(32, "big") for v in row) for row in rows)
     B = len(rows)
     out = ctypes.create_string_buffer(48 * B)
     status = (ctypes.c_int * B)()
-    assert msm.shim_commit(g1, 4, c, blobs, B, out, status, T, k) == 0
+    assert msm.shim_commit(g1, 4, g, blobs, B, out, status, T, k) == 0
     from oracle.binding import OracleError
     for i in range(B):
         try:
@@ -131,6 +152,26 @@ def test_commit_pipeline_on_cpu_minimal_preset(msm, c, T, k):
             assert status[i] == 1
             continue
         assert status[i] == 0 and out.raw[48 * i:48 * i + 48] == exp, i
+
+
+@pytest.mark.parametrize("n,g", [(7, 3), (11, 4), (13, 5), (6, 6), (10, 7)])
+def test_comb_msm_vs_plain_ladder(msm, n, g):
+    """The comb over point counts that leave an odd number of groups, a padded last group and odd tree rows,
+    on the first n mainnet setup points, against sum_i [s_i]P_i by double-and-add."""
+    g1 = golden().g1_bytes[:48 * n]
+    rng = np.random.default_rng(n * 100 + g)
+    rows = [[0] * n, [1] * n, [R - 1] * n, [2] * n, [(i + 1) for i in range(n)]]
+    rows += [[int.from_bytes(rng.bytes(32), "big") % R for _ in range(n)] for _ in range(2)]
+    B = len(rows)
+    sc = (ctypes.c_uint32 * (B * n * 8))()
+    for b, row in enumerate(rows):
+        for i, v in enumerate(row):
+            for w in range(8):
+                sc[(b * n + i) * 8 + w] = (v >> (32 * w)) & 0xffffffff
+    oc, ol = ctypes.create_string_buffer(48 * B), ctypes.create_string_buffer(48 * B)
+    assert msm.shim_msm_vs_ladder(g1, n, g, sc, B, oc, ol, 8, 5) == 0
+    assert oc.raw == ol.raw
+    assert oc.raw[:48] == bytes([0xc0]) + bytes(47)
 
 
 def test_library_exports_every_declared_symbol():

@@ -46,7 +46,7 @@ def bench(name, fn, n_elems=None, reps=samples):
         ts.append(time.perf_counter() - t0)
     med = statistics.median(ts)
     line = {"bench": name, "median_ms": round(med * 1e3, 4), "min_ms": round(min(ts) * 1e3, 4), "samples": reps,
-            "window_bits": s.window_bits}
+            "comb_width": s.comb_width}
     if n_elems:
         line["elements_per_s"] = round(n_elems / med, 1)
     print(json.dumps(line), flush=True)

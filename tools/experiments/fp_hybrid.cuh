@@ -22,7 +22,7 @@
 // Host build: the same code with fma() under FE_TOWARDZERO (tests/hostshim), so the limb
 // algebra is checked against Python integers on a CPU.
 #pragma once
-#include "fields.cuh"
+#include "../../kzg_rust_b200/csrc/fields.cuh"
 
 #if !defined(__CUDA_ARCH__)
 #include <cfenv>

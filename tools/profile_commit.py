@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Short commit run for `ncu --set full` captures (not part of the product).
 
-    python tools/profile_commit.py [window_bits] [blobs] [calls]
+    python tools/profile_commit.py [comb_width] [blobs] [calls]
 
 Creates a context, then runs `kzg_b200_blob_to_kzg_commitment_device` `calls` times over the
 same device-resident synthetic blobs.  One call over <= 4096 blobs is one chunk: 1 digit
@@ -36,5 +36,5 @@ for _ in range(calls):
     assert rc == 0, rc
     L.kzg_b200_synchronize(s._h)
 assert not bool(st.any().item())
-print("profile_commit ok: c=%d n=%d calls=%d" % (s.window_bits, n, calls))
+print("profile_commit ok: c=%d n=%d calls=%d" % (s.comb_width, n, calls))
 s.close()

@@ -9,7 +9,7 @@
 #include <cstdlib>
 
 #include "../kzg_rust_b200/csrc/fields.cuh"
-#include "../kzg_rust_b200/csrc/fp_hybrid.cuh"
+#include "experiments/fp_hybrid.cuh"
 
 using namespace kzg;
 

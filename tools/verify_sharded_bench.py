@@ -85,7 +85,7 @@ if rank == 0:
     print(json.dumps({"metric": "verify_blob_kzg_proof_batch throughput (sharded, one verdict)", "value": n_total / best,
                       "unit": "blobs/s", "n_gpus": world, "blobs": n_total, "ms_per_call": best * 1e3,
                       "all_ms": [round(t * 1e3, 2) for t in times], "negative_control_rejected": True,
-                      "window_bits": s.window_bits, "timing": "wall clock around the blocking call, max over ranks, host buffers"}), flush=True)
+                      "comb_width": s.comb_width, "timing": "wall clock around the blocking call, max over ranks, host buffers"}), flush=True)
 s.close()
 if world > 1:
     dist.destroy_process_group()
