@@ -6,6 +6,6 @@ created from."""
 from .kzg import (BYTES_PER_COMMITMENT, BYTES_PER_FIELD_ELEMENT, BYTES_PER_G1, BYTES_PER_G2, BYTES_PER_PROOF,
                   TRUSTED_SETUP_NUM_G2_POINTS, BadArgs, Blob, BlobMinimal, Bytes32, Bytes48, CudaError, Error,
                   InternalError, InvalidBytesLength, InvalidHexFormat, InvalidTrustedSetup, Kzg, KzgCommitment,
-                  KzgProof, KzgSettings, hex_to_bytes, load_library)
+                  KzgProof, KzgSettings, TrustedSetup, hex_to_bytes, load_library)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

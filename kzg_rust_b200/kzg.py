@@ -237,6 +237,61 @@ class KzgSettings:
         self.close()
 
 
+class TrustedSetup:
+    """reference `TrustedSetup` (src/trusted_setup.rs:13-44, 138-153): the trusted setup in the json format of the
+    ethereum consensus specs -- {"setup_G1_lagrange": [hex, ...], "setup_G2": [hex, ...]}, hex with or without 0x.
+    The G1 list is truncated to the preset's FIELD_ELEMENTS_PER_BLOB after parsing, as the reference does."""
+
+    def __init__(self, g1_points, g2_points):
+        self._g1 = [bytes(p) for p in g1_points]
+        self._g2 = [bytes(p) for p in g2_points]
+
+    @staticmethod
+    def _point(v, size, what):
+        if not isinstance(v, str):
+            raise InvalidTrustedSetup("A %d byte hex encoded string" % size)
+        try:
+            b = bytes.fromhex(v[2:] if v.startswith("0x") else v)
+        except ValueError as e:
+            raise InvalidTrustedSetup("Failed to decode %s point: %s" % (what, e))
+        if len(b) != size:
+            raise InvalidTrustedSetup("%s point has invalid length. Expected %d got %d" % (what, size, len(b)))
+        return b
+
+    @classmethod
+    def from_json(cls, text, field_elements_per_blob=4096):
+        import json
+        try:
+            doc = json.loads(text)
+            g1, g2 = doc["setup_G1_lagrange"], doc["setup_G2"]
+        except (ValueError, KeyError, TypeError) as e:
+            raise InvalidTrustedSetup("not a trusted setup in json form: %s" % e)
+        g1 = [cls._point(v, BYTES_PER_G1, "G1") for v in g1][:field_elements_per_blob]
+        g2 = [cls._point(v, BYTES_PER_G2, "G2") for v in g2]
+        return cls(g1, g2)
+
+    @classmethod
+    def from_json_file(cls, path, field_elements_per_blob=4096):
+        with open(path) as fh:
+            return cls.from_json(fh.read(), field_elements_per_blob)
+
+    def to_json(self):
+        import json
+        return json.dumps({"setup_G1_lagrange": [p.hex() for p in self._g1], "setup_G2": [p.hex() for p in self._g2]})
+
+    def g1_points(self):
+        return list(self._g1)
+
+    def g2_points(self):
+        return list(self._g2)
+
+    def g1_len(self):
+        return len(self._g1)
+
+    def g2_len(self):
+        return len(self._g2)
+
+
 def _np_u8(buf, nbytes):
     a = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf.reshape(-1).view(np.uint8)
     if a.size != nbytes:

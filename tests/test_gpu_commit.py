@@ -209,3 +209,17 @@ def test_every_commitment_of_a_large_batch_by_the_tau_identity():
     out[3] = 0
     got = out[8:8 + 32].cpu().numpy()
     assert not est.any() and np.array_equal(got, exp)
+
+
+def test_trusted_setup_json_to_settings():
+    """reference `TrustedSetup` (src/trusted_setup.rs): json -> g1_points / g2_points -> load_trusted_setup."""
+    import json
+    k = _kzg()
+    doc = {"setup_G1_lagrange": ["0x" + G.g1_bytes[48 * i:48 * i + 48].hex() for i in range(4096)],
+           "setup_G2": [G.g2_bytes[96 * i:96 * i + 96].hex() for i in range(65)]}
+    ts = k.TrustedSetup.from_json(json.dumps(doc))
+    s = k.Kzg.load_trusted_setup(ts.g1_points(), ts.g2_points(), 0, 5)
+    case = next(c for c in G.by_fn("blob_to_kzg_commitment") if c["output"] is not None)
+    out = k.Kzg.blob_to_kzg_commitment(k.Blob.from_bytes(G.get_bytes(case["input"]["blob"])), s)
+    assert "0x" + out.to_bytes().hex() == case["output"]
+    s.close()

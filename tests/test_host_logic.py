@@ -362,3 +362,28 @@ def test_unconditional_lazy_subtraction_and_wide_products(field):
         got = _unpack(r)
         assert all(g < 2 * P for g in got)
         assert [g % P for g in got] == [x * y * Rinv % P for x, y in zip(fv, sv)]
+
+
+def test_trusted_setup_json_helper():
+    """reference `TrustedSetup` (src/trusted_setup.rs:21-44, 138-153): the consensus-specs json form, with and
+    without 0x, truncated to the preset's FIELD_ELEMENTS_PER_BLOB; malformed points are rejected."""
+    import json
+    import kzg_rust_b200 as k
+    g = golden()
+    g1 = [g.g1_bytes[48 * i:48 * i + 48] for i in range(4096)]
+    g2 = [g.g2_bytes[96 * i:96 * i + 96] for i in range(65)]
+    doc = {"setup_G1": ["0x" + "00" * 48], "setup_G1_lagrange": ["0x" + p.hex() for p in g1], "setup_G2": [p.hex() for p in g2]}
+    ts = k.TrustedSetup.from_json(json.dumps(doc))
+    assert ts.g1_len() == 4096 and ts.g2_len() == 65
+    assert ts.g1_points() == g1 and ts.g2_points() == g2
+    assert k.TrustedSetup.from_json(ts.to_json()).g1_points() == g1
+    small = k.TrustedSetup.from_json(json.dumps(doc), field_elements_per_blob=4)
+    assert small.g1_len() == 4 and small.g1_points() == g1[:4] and small.g2_len() == 65
+    bad = dict(doc, setup_G2=[g2[0].hex()[:-2]] + doc["setup_G2"][1:])
+    with pytest.raises(k.InvalidTrustedSetup):
+        k.TrustedSetup.from_json(json.dumps(bad))
+    bad = dict(doc, setup_G1_lagrange=["0xzz" + "00" * 47] + doc["setup_G1_lagrange"][1:])
+    with pytest.raises(k.InvalidTrustedSetup):
+        k.TrustedSetup.from_json(json.dumps(bad))
+    with pytest.raises(k.InvalidTrustedSetup):
+        k.TrustedSetup.from_json("{}")
