@@ -7,15 +7,21 @@
 A "step" is one pass of `blob_to_kzg_commitment` over one batch of synthetic blobs
 (BASELINE.json configs[3]: 65,536 blobs; reference generator benches/kzg_benches.rs:14-23).
 Blobs are independent, so every rank processes its own batch with its own context and there is
-no data-path collective (weak scaling); the only collective is the barrier / max-reduce of the
-timings.
+no data-path collective (weak scaling); the only collectives of the headline are the barrier / max-reduce of
+the timings.
 
   value      whole-job blobs/s with the blobs already resident in HBM (device entry point)
   e2e        the same through the host-buffer C ABI call (kzg_b200_blob_to_kzg_commitment_batch):
              pinned host blobs -> H2D -> kernels -> D2H of commitments + status, all timed
+  parity     every commitment of the last timed step checked on the device by C == [p(tau)] G1 (tau = 1337, the
+             bundled testing setup; an independent ladder, kzg_b200_debug_check_tau_identity) on every rank, plus the
+             byte comparison with the CPU oracle on a sample (rank 0, N = 1)
   roofline   the MSM kernel (batch_add_kernel, all instantiations) against the measured
              integer-multiply issue rate; per-stage device times come from CUDA events on
              the context's stream (kzg_b200_profile_*)
+  also       compute_blob_kzg_proof (device-resident), the strong-scaling leg (BASELINE.json configs[3] as stated:
+             65,536 blobs in total, sharded), verify_blob_kzg_proof_batch at 6 / 1024 / 4096 / 16,384 blobs (configs[2]),
+             the sharded 16,384-blob verification when N > 1 (configs[4]), and the table-size trade-off
   cpu_baseline / --impl reference
              the CPU restatement (oracle/, a port: the crate's blst path cannot be built here)
              on the box's host cores
@@ -38,8 +44,18 @@ BYTES_PER_BLOB = 131072
 # BASELINE.md section 3 (fixed constants): algorithmic integer-multiply work per blob
 IMAD_PER_COMMIT = 3.24e8
 IMAD_PER_PROOF = 3.34e8
+IMAD_PER_VERIFY = 8.4e6
 HBM_BYTES_PER_COMMIT = 131120
 STAGES = ["digits", "msm_gather", "msm_tree", "compress", "challenge", "eval", "validate", "verify_terms"]
+DTYPE = "u32 limbs (381-bit Fp / 255-bit Fr integers)"
+
+
+def workload_config(blobs):
+    """`config` is the same in both arms (the reference arm times a bounded sample of this workload per step)."""
+    return {"workload": "mainnet blob_to_kzg_commitment, %d synthetic blobs per GPU per step (BASELINE.json configs[3]), "
+                        "trusted_setup.txt" % blobs,
+            "blobs_per_gpu_per_step": blobs,
+            "l2": "inputs (%.1f GiB per step) exceed L2" % (blobs * BYTES_PER_BLOB / 2 ** 30)}
 
 
 def read_setup():
@@ -54,6 +70,18 @@ def measured_peaks():
         with open(p) as fh:
             return json.load(fh), "measured"
     return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def ncu_traffic(comb_width):
+    """DRAM bytes per average batch_add launch, from the committed ncu capture of this code (profiles/ncu_traffic.json,
+    written by tools/summarize_ncu.py from `ncu --set full`); None when no capture matches the configuration."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as fh:
+        doc = json.load(fh)
+    rec = doc.get(str(comb_width))
+    return (rec["dram_bytes_per_avg_launch"], rec.get("source")) if rec else (None, None)
 
 
 class ClockSampler:
@@ -78,9 +106,6 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def mark(self):
-        return time.time()
-
     def stop(self):
         if self.proc:
             self.proc.terminate()
@@ -101,32 +126,44 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(rows)}
 
 
+def cpu_sample_size(cores):
+    return 64 * cores  # some 10-30 s of CPU work per step
+
+
+def cpu_commit(o, blobs, cores):
+    """The CPU arm's path: the fast restatement when the oracle library has it, else the checker path."""
+    fast = getattr(o, "blob_to_kzg_commitment_many_fast", None)
+    if fast is not None:
+        return fast(blobs, nthreads=cores), "fast"
+    return o.blob_to_kzg_commitment_many(blobs, nthreads=cores), "checker"
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the CPU restatement of the reference's path on the host cores."""
+    """--impl reference: the CPU restatement of the reference's path on the host cores, on a bounded sample of the
+    GPU arm's workload per step (the same sample size as the GPU arm's cpu_baseline leg)."""
     if rank != 0:
         return
-    import numpy as np
     from gpu_util import oracle_settings, synthetic_blobs
     cores = os.cpu_count() or 1
     o = oracle_settings("mainnet")
-    per_step = 16 * cores  # ~2 s per step at ~7 blobs/s/core
+    per_step = cpu_sample_size(cores)
     blobs = synthetic_blobs(per_step, seed=0xB200)
     for _ in range(max(1, min(args.warmup, 1))):
-        o.blob_to_kzg_commitment_many(blobs[:cores], nthreads=cores)
+        cpu_commit(o, blobs[:cores], cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out, st = o.blob_to_kzg_commitment_many(blobs, nthreads=cores)
+        (out, st), kind = cpu_commit(o, blobs, cores)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
-    sample = "%d blobs per step x %d steps, one blob per thread on %d threads" % (per_step, args.steps, cores)
+    sample = "%d blobs of the workload per step x %d steps, one blob per thread on %d threads" % (per_step, args.steps, cores)
     print(json.dumps({
         "impl": "reference", "metric": "blob_to_kzg_commitment throughput", "value": value, "unit": "blobs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit Fp / 255-bit Fr integers)",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
         "data": "synthetic",
-        "config": {"workload": "mainnet blob_to_kzg_commitment, synthetic blobs (top byte of each element zero), trusted_setup.txt"},
-        "cpu_baseline": {"value": value, "unit": "blobs/s", "cores": cores, "kind": "port", "sample": sample,
-                         "note": "CPU restatement (oracle/kzg_oracle.c), not blst: cargo/rustc and the blst sources are absent here"},
+        "config": workload_config(args.blobs),
+        "cpu_baseline": {"value": value, "unit": "blobs/s", "cores": cores, "kind": "port", "sample": sample, "path": kind,
+                         "note": "CPU restatement (oracle/), not blst: cargo/rustc and the blst sources are absent here"},
         "e2e": {"value": value, "unit": "blobs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -140,8 +177,9 @@ def main():
     ap.add_argument("--blobs", type=int, default=int(os.environ.get("KZG_BENCH_BLOBS", 65536)), help="blobs per GPU per step")
     ap.add_argument("--host-pool", type=int, default=65536, help="pinned host blobs per end-to-end call (the user's batch; 8 GiB pinned at 65536)")
     ap.add_argument("--comb-width", type=int, default=0, help="setup points per table group (0 = automatic)")
-    ap.add_argument("--no-proof", action="store_true", help="skip the compute_blob_kzg_proof side measurement")
+    ap.add_argument("--no-proof", action="store_true", help="skip the compute_blob_kzg_proof / verification side measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the table-size trade-off (other comb widths)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
@@ -155,6 +193,7 @@ def main():
     import torch
     import torch.distributed as dist
     import kzg_rust_b200 as k
+    from kzg_rust_b200 import sharded
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
@@ -169,6 +208,7 @@ def main():
     t_create = time.time()
     s = k.KzgSettings.load_trusted_setup(g1, g2, local_rank, args.comb_width)
     t_create = time.time() - t_create
+    comb_width, table_gb = s.comb_width, round(s.table_bytes / 1e9, 1)
     stream = torch.cuda.ExternalStream(L.kzg_b200_stream(s._h), device=dev)
     B = args.blobs
 
@@ -178,12 +218,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def max_over_ranks(ms):
+    def reduce_over_ranks(v, op):
         if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
         return float(t.item())
+
+    def max_over_ranks(ms):
+        return reduce_over_ranks(ms, dist.ReduceOp.MAX)
 
     # synthetic blobs on the device (reference generator: uniform bytes, top byte of each element 0)
     gen = torch.Generator(device=dev)
@@ -197,8 +240,8 @@ def main():
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     proofs = torch.zeros((B, 48), dtype=torch.uint8, device=dev)
 
-    def commit_device():
-        rc = L.kzg_b200_blob_to_kzg_commitment_device(s._h, blobs.data_ptr(), B, out.data_ptr(), status.data_ptr())
+    def commit_device(count=B, first=0):
+        rc = L.kzg_b200_blob_to_kzg_commitment_device(s._h, blobs[first:].data_ptr(), count, out[first:].data_ptr(), status[first:].data_ptr())
         if rc:
             raise SystemExit("kzg_b200_blob_to_kzg_commitment_device failed: %d" % rc)
 
@@ -225,6 +268,16 @@ def main():
         barrier()
         return max_over_ranks(e0.elapsed_time(e1)), L.kzg_b200_launch_count(s._h) - l0, (w0, w1)
 
+    def timed_wall(fn, reps):
+        """blocking host-side calls (verification ends with a host pairing): wall clock, max over ranks"""
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        dt = (time.perf_counter() - t0) / reps
+        barrier()
+        return max_over_ranks(dt * 1e3)
+
     clocks = ClockSampler(local_rank) if rank == 0 and not os.environ.get("KZG_BENCH_NO_CLOCKS") else None
 
     # ---- device-resident leg (value)
@@ -233,6 +286,20 @@ def main():
         raise SystemExit("synthetic blobs were rejected")
     value = world * B * args.steps / (ms * 1e-3)
     clock_summary = clocks.summary(w0, w1) if clocks else None
+
+    # ---- parity of the timed step's output: every commitment on every rank by the tau identity
+    ok = torch.zeros(B, dtype=torch.int32, device=dev)
+    tau = (1337).to_bytes(32, "big")
+    t0 = time.perf_counter()
+    rc = L.kzg_b200_debug_check_tau_identity(s._h, blobs.data_ptr(), out.data_ptr(), B, tau, ok.data_ptr())
+    if rc:
+        raise SystemExit("kzg_b200_debug_check_tau_identity failed: %d" % rc)
+    tau_ok = int(reduce_over_ranks(float(ok.sum().item()), dist.ReduceOp.SUM))
+    tau_s = time.perf_counter() - t0
+    if tau_ok != world * B:
+        raise SystemExit("tau identity failed on %d of %d commitments" % (world * B - tau_ok, world * B))
+    out_ref = out.clone()
+
     # one more step with per-stage CUDA-event timing (profiling runs the chunks one at a time, so
     # the stage times do not overlap; the timed steps above keep two chunks in flight)
     L.kzg_b200_profile_enable(s._h, 1)
@@ -241,6 +308,15 @@ def main():
     stage_ln = (ctypes.c_uint64 * 8)()
     L.kzg_b200_profile_read(s._h, stage_ms, stage_ln)
     L.kzg_b200_profile_enable(s._h, 0)
+
+    # ---- strong-scaling leg: BASELINE.json configs[3] as stated -- 65,536 blobs in total, contiguous shards
+    lo, hi = sharded.shard_range(B, rank, world)
+    strong_ms, _, _ = timed(lambda: commit_device(hi - lo, lo), args.steps, 1)
+    strong = {"metric": "blob_to_kzg_commitment throughput, %d blobs in total sharded over %d GPU(s)" % (B, world),
+              "value": B * args.steps / (strong_ms * 1e-3), "unit": "blobs/s", "scaling": "strong", "steps": args.steps,
+              "ms_per_step": strong_ms / args.steps, "blobs_per_gpu_per_step": hi - lo}
+    if not bool((out == out_ref).all().item()):
+        raise SystemExit("sharded run changed commitments")
 
     # ---- end-to-end leg: pinned host blobs through the host-buffer C ABI call
     pool = min(args.host_pool, B)
@@ -276,32 +352,61 @@ def main():
         if int(status.any().item()):
             raise SystemExit("proof path rejected synthetic blobs")
         proof = {"metric": "compute_blob_kzg_proof throughput", "value": world * B / (pms * 1e-3), "unit": "blobs/s",
-                 "steps": 1, "warmup": 1, "ms_per_step": pms,
-                 "imad_roofline_frac": None}
-    # ---- verify_blob_kzg_proof_batch side measurement (BASELINE.json configs[2]: 6 and 1024 blobs),
-    # host buffers through kzg_b200_verify_blob_kzg_proof_batch, wall clock around the blocking call
-    verify = None
-    if proof is not None and rank == 0:
-        nv = min(1024, B)
+                 "steps": 1, "warmup": 1, "ms_per_step": pms, "imad_roofline_frac": None}
+
+    # ---- verify_blob_kzg_proof_batch (BASELINE.json configs[2] and configs[4])
+    verify, verify_sharded = None, None
+    if proof is not None:
+        nv_max = min(16384, B)
         pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t).numpy()
-        vb = pin(blobs[:nv].reshape(nv, BYTES_PER_BLOB))
-        vc, vp = pin(out[:nv]), pin(proofs[:nv])
-        verify = {}
-        for n_v, reps in ((6, 5), (nv, 2)):
-            if not k.Kzg.verify_blob_kzg_proof_batch_raw(vb[:n_v], vc[:n_v], vp[:n_v], n_v, s):
-                raise SystemExit("verify_blob_kzg_proof_batch rejected proofs made by the path itself")
+        vb = pin(blobs[:nv_max].reshape(nv_max, BYTES_PER_BLOB))
+        vc, vp = pin(out[:nv_max]), pin(proofs[:nv_max])
+        if rank == 0:
+            verify = {}
+            for n_v, reps in sorted({(6, 10), (min(1024, B), 3), (min(4096, B), 2), (nv_max, 2)}):
+                if not k.Kzg.verify_blob_kzg_proof_batch_raw(vb[:n_v], vc[:n_v], vp[:n_v], n_v, s):
+                    raise SystemExit("verify_blob_kzg_proof_batch rejected proofs made by the path itself")
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    k.Kzg.verify_blob_kzg_proof_batch_raw(vb[:n_v], vc[:n_v], vp[:n_v], n_v, s)
+                dt = (time.perf_counter() - t0) / reps
+                verify["n=%d" % n_v] = {"ms_per_call": dt * 1e3, "blobs_per_s": n_v / dt, "buffers": "pinned host"}
+            okc = ctypes.c_int(0)
+            call = lambda: L.kzg_b200_verify_blob_kzg_proof_batch_device(s._h, blobs.data_ptr(), out.data_ptr(), proofs.data_ptr(), nv_max, ctypes.byref(okc))
+            if call() or not okc.value:
+                raise SystemExit("device-resident verification rejected proofs made by the path itself")
             t0 = time.perf_counter()
-            for _ in range(reps):
-                k.Kzg.verify_blob_kzg_proof_batch_raw(vb[:n_v], vc[:n_v], vp[:n_v], n_v, s)
-            dt = (time.perf_counter() - t0) / reps
-            verify["n=%d" % n_v] = {"ms_per_call": dt * 1e3, "blobs_per_s": n_v / dt}
-        bad = vp[:6].copy()
-        bad[[0, 5]] = bad[[5, 0]]
-        verify["negative_control_rejected"] = not k.Kzg.verify_blob_kzg_proof_batch_raw(vb[:6], vc[:6], bad, 6, s)
+            for _ in range(3):
+                call()
+            dt = (time.perf_counter() - t0) / 3
+            verify["n=%d device-resident" % nv_max] = {"ms_per_call": dt * 1e3, "blobs_per_s": nv_max / dt, "buffers": "HBM"}
+            bad = vp[:6].copy()
+            bad[[0, 5]] = bad[[5, 0]]
+            verify["negative_control_rejected"] = not k.Kzg.verify_blob_kzg_proof_batch_raw(vb[:6], vc[:6], bad, 6, s)
+        # configs[4]: one verdict for 16,384 blobs sharded over the ranks (two small all_gathers + one host pairing)
+        if world > 1:
+            n_tot = nv_max
+            be = sharded.CudaBackend(s)
+            vlo, vhi = sharded.shard_range(n_tot, rank, world)
+            # rank r holds blobs [vlo, vhi) of the batch (its own synthetic blobs, commitments and proofs)
+            sb, sc, sp = vb[vlo:vhi], vc[vlo:vhi], vp[vlo:vhi]
+            good = sharded.verify_blob_kzg_proof_batch_sharded(be, sb, sc, sp, n_tot, device=dev)
+            vms = timed_wall(lambda: sharded.verify_blob_kzg_proof_batch_sharded(be, sb, sc, sp, n_tot, device=dev), 2)
+            sp_bad = sp.copy()
+            if rank == world - 1:
+                sp_bad[[0, 1]] = sp_bad[[1, 0]]
+            tampered = sharded.verify_blob_kzg_proof_batch_sharded(be, sb, sc, sp_bad, n_tot, device=dev)
+            verify_sharded = {"blobs": n_tot, "gpus": world, "ms_per_verdict": vms, "blobs_per_s": n_tot / (vms * 1e-3),
+                              "accepted": bool(good), "tampered_rejected": not tampered,
+                              "exchange": "2 all_gathers per verdict: 160 B per blob (C, z, y, proof) + status, then 225 B per rank",
+                              "timing": "wall clock around the blocking call (it ends with a host pairing), max over ranks"}
+            if not good or tampered:
+                raise SystemExit("sharded verification gave the wrong verdict")
     if clocks:
         clocks.stop()
 
     if rank != 0:
+        s.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -314,30 +419,27 @@ def main():
     msm_launches = int(stage_ln[1] + stage_ln[2])
     blobs_timed = B  # the profiled step
     achieved = IMAD_PER_COMMIT * blobs_timed / (msm_ms * 1e-3) if msm_ms > 0 else 0.0
-    groups = -(-4096 // s.comb_width)
+    groups = -(-4096 // comb_width)
     # what this design executes per blob: 255 bit positions x (groups - 1) affine additions x 6 products, plus the
     # Horner pass (254 doublings at 7 products + 254 mixed additions at 11); 600 IMAD issue slots per product
-    executed_imad = (255 * (groups - 1) * 6 + 254 * 18) * 600.0
-    wn = None
+    additions = 255 * (groups - 1)
+    executed_imad = (additions * 6 + 254 * 18) * 600.0
+    traffic, traffic_src = ncu_traffic(comb_width)
     roofline = {
-        "bound": "imad", "kernel": "batch_add_kernel (GatherPolicy + TreePolicy launches)",
+        "bound": "imad", "kernel": "batch_add_kernel (GatherPolicy + PairPolicy launches)",
         "achieved": achieved / 1e12, "peak": imad.value / 1e12, "unit": "TIMAD/s", "frac": achieved / imad.value if imad.value else None,
-        # DRAM bytes per average launch, from `ncu --set full` of one gather-level and one level-1 launch of a
-        # 4096-blob chunk at c = 19 (profiles/ncu_batch_add_r1c.md: 99.8 GB and 33.8 GB read + written);
-        # levels 2..11 halve each time, 12 launches per chunk.  The MSM streams the selected table rows and the
-        # intermediate levels through HBM by design (40 % of the HBM peak) to do 36 % fewer additions.
-        "traffic": None,
-        "traffic_unit": "DRAM bytes per average batch_add launch (ncu, 4096-blob chunk)",
+        "traffic": traffic, "traffic_unit": "DRAM bytes per average batch_add launch (ncu --set full, 4096-blob chunk)", "traffic_source": traffic_src,
         "launches": msm_launches, "avg_launch_ms": msm_ms / max(1, msm_launches),
         "algorithmic_imad_per_blob": IMAD_PER_COMMIT,
         "peak_source": "mad.lo.u32 issue-rate micro-benchmark run in this process (kzg_b200_measure_peaks); "
                        "MEASURED_PEAKS.json has no integer figure",
         "wide_mac_per_s": imadw.value, "fp_mul_per_s": fpmul.value,
         "whole_step_frac": IMAD_PER_COMMIT * value / world / imad.value if imad.value else None,
-        # against the work this design actually executes: W windows x (n - 1) additions x 6 products x 600 IMAD slots
-        "executed_imad_per_blob": executed_imad,
+        # against the work this design actually executes
+        "additions_per_blob": additions, "executed_imad_per_blob": executed_imad,
         "executed_frac": executed_imad * blobs_timed / (msm_ms * 1e-3) / imad.value if imad.value and msm_ms > 0 else None,
         "executed_whole_step_frac": executed_imad * value / world / imad.value if imad.value else None,
+        "additions_per_s": additions * blobs_timed / (msm_ms * 1e-3) if msm_ms > 0 else None,
         "hbm": {"achieved_gbs": HBM_BYTES_PER_COMMIT * value / world / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                 "frac": HBM_BYTES_PER_COMMIT * value / world / 1e9 / peaks.get("hbm_gbs", 1.0), "peak_kind": peaks_kind},
         "stage_ms_per_step": {STAGES[i]: stage_ms[i] for i in range(8) if stage_ms[i] > 0},
@@ -345,46 +447,80 @@ def main():
     }
     if proof is not None and imad.value:
         proof["imad_roofline_frac"] = IMAD_PER_PROOF * proof["value"] / world / imad.value
+    if verify is not None and imad.value:
+        for rec in verify.values():
+            if isinstance(rec, dict):
+                rec["imad_roofline_frac"] = IMAD_PER_VERIFY * rec["blobs_per_s"] / imad.value
 
-    # ---- CPU baseline (bounded sample) + parity spot check of the GPU output against it
+    # ---- CPU baseline (bounded sample, N = 1 only) + byte comparison of the GPU output with the checker
     cpu = None
+    parity = "%d/%d commitments by the tau identity on the device (%.1f s)" % (tau_ok, world * B, tau_s)
     if not args.no_cpu and world == 1:
         from gpu_util import oracle_settings
         cores = os.cpu_count() or 1
         o = oracle_settings("mainnet")
-        nsamp = min(B, 64 * cores)  # ~10 s of CPU work at ~7 blobs/s/core
+        nsamp = min(B, cpu_sample_size(cores))
         sample = blobs[:nsamp].reshape(nsamp, BYTES_PER_BLOB).cpu().numpy()
-        o.blob_to_kzg_commitment_many(sample[:cores], nthreads=cores)
+        cpu_commit(o, sample[:cores], cores)
         t0 = time.perf_counter()
-        exp, est = o.blob_to_kzg_commitment_many(sample, nthreads=cores)
+        (exp, est), kind = cpu_commit(o, sample, cores)
         dt = time.perf_counter() - t0
         got = out[:nsamp].cpu().numpy()
         if est.any() or not np.array_equal(got, exp):
             raise SystemExit("GPU commitments differ from the CPU oracle on the sampled blobs")
-        cpu = {"value": nsamp / dt, "unit": "blobs/s", "cores": cores, "kind": "port",
+        cpu = {"value": nsamp / dt, "unit": "blobs/s", "cores": cores, "kind": "port", "path": kind,
                "sample": "first %d blobs of the batch, one blob per thread on %d threads (%.1f s)" % (nsamp, cores, dt),
                "parity": "GPU commitments byte-equal on the sample",
-               "note": "CPU restatement (oracle/kzg_oracle.c), not blst"}
+               "note": "CPU restatement (oracle/), not blst"}
+        parity += " + %d byte-equal with the CPU oracle" % nsamp
+
+    # ---- table size against throughput: the other comb widths on a 16,384-blob batch (N = 1 only)
+    tradeoff = None
+    if not args.no_sweep and world == 1 and args.comb_width == 0:
+        tradeoff = [{"comb_width": comb_width, "table_gb": table_gb, "additions_per_blob": additions, "blobs_per_s": value,
+                     "note": "the timed configuration (default rule: the widest comb whose table takes at most half of the free memory)"}]
+        s.close()
+        s = None
+        nb = min(B, 16384)
+        for g in (22, 21, 20):
+            sg = k.KzgSettings.load_trusted_setup(g1, g2, local_rank, g)
+            stg = torch.cuda.ExternalStream(L.kzg_b200_stream(sg._h), device=dev)
+            run = lambda: L.kzg_b200_blob_to_kzg_commitment_device(sg._h, blobs.data_ptr(), nb, out.data_ptr(), status.data_ptr())
+            run()
+            L.kzg_b200_synchronize(sg._h)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stg)
+            run()
+            run()
+            e1.record(stg)
+            e1.synchronize()
+            L.kzg_b200_synchronize(sg._h)
+            tradeoff.append({"comb_width": g, "table_gb": round(sg.table_bytes / 1e9, 1), "additions_per_blob": 255 * (-(-4096 // g) - 1),
+                             "blobs_per_s": 2 * nb / (e0.elapsed_time(e1) * 1e-3),
+                             "same_bytes": bool((out[:nb] == out_ref[:nb]).all().item())})
+            sg.close()
 
     line = {
         "metric": "blob_to_kzg_commitment throughput", "value": value, "unit": "blobs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit Fp / 255-bit Fr integers)", "data": "synthetic",
-        "config": {"workload": "mainnet blob_to_kzg_commitment, %d synthetic blobs per GPU per step (BASELINE.json configs[3]), "
-                               "trusted_setup.txt" % B,
-                   "blobs_per_gpu_per_step": B, "comb_width": s.comb_width, "table_gb": round(s.table_bytes / 1e9, 1), "chunk_blobs": s.chunk_blobs, "sharding": "independent blobs, one context per GPU, no collective",
-                   "l2": "inputs (%.1f GiB per step) exceed L2" % (B * BYTES_PER_BLOB / 2 ** 30), "ctx_create_s": round(t_create, 2)},
+        "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": workload_config(B),
+        "b200": {"comb_width": comb_width, "table_gb": table_gb, "additions_per_blob": additions,
+                 "sharding": "independent blobs, one context per GPU, no collective", "ctx_create_s": round(t_create, 2)},
         "e2e": {"value": e2e_value, "unit": "blobs/s", "h2d_bytes_per_step": calls * pool * BYTES_PER_BLOB,
                 "d2h_bytes_per_step": calls * pool * 52, "ms_per_step": e2e_ms / args.steps,
                 "api": "kzg_b200_blob_to_kzg_commitment_batch on pinned host buffers, %d calls of %d blobs per step" % (calls, pool)},
         "gpu_launches": int(launches),
+        "parity": parity,
         "clocks": clock_summary,
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "also": {"compute_blob_kzg_proof": proof, "verify_blob_kzg_proof_batch": verify},
+        "also": {"compute_blob_kzg_proof": proof, "strong_scaling": strong, "verify_blob_kzg_proof_batch": verify,
+                 "verify_blob_kzg_proof_batch_sharded": verify_sharded, "comb_width_tradeoff": tradeoff},
     }
     print(json.dumps(line), flush=True)
-    s.close()
+    if s is not None:
+        s.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -17,7 +17,7 @@
  *     blob, so one bad blob does not poison the batch; the single-blob Rust methods map a
  *     non-zero status[0] to `Err`.
  *   - A context plays the role of `KzgSettings` (src/kzg.rs:27-40) and owns all device memory
- *     (the precomputed multiples of the Lagrange points, roots of unity, workspaces).  It is
+ *     (the precomputed signed sums of the Lagrange points, roots of unity, workspaces).  It is
  *     bound to one GPU; multi-GPU use is one context (and one process) per GPU with the blob
  *     range sharded by the caller.  Calls on one context are serialised internally, so it may
  *     be shared between host threads like `&KzgSettings`.
@@ -132,6 +132,9 @@ int kzg_b200_verify_kzg_proof(kzg_b200_ctx *ctx, const uint8_t commitment[48], c
  *   with A_g = sum r^i proof_i, B_g = sum r^i C_i + sum r^i z_i proof_i, s_g = sum r^i y_i.
  * kzg_b200_verify_finish adds the partial sums of all shards and runs the final check
  * e(A, [tau]G2) == e(B - [s]G1, G2) on the host (reference src/kzg.rs:618-625).
+ * Phase B trusts nothing it is handed: commitments and proofs are decompressed and subgroup-checked again, z_i and
+ * y_i must be canonical field elements (KZG_B200_BAD_ARGS otherwise), so it is safe on re-fetched data or on another
+ * context than phase A's.
  */
 int kzg_b200_verify_phase_a(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments,
                             const uint8_t *proofs, size_t n, uint8_t *zy_out);
@@ -153,6 +156,11 @@ int kzg_b200_blob_to_kzg_commitment_device(kzg_b200_ctx *ctx, const uint8_t *d_b
 int kzg_b200_compute_blob_kzg_proof_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments,
                                            size_t n, uint8_t *d_proofs_out, int32_t *d_status);
 int kzg_b200_synchronize(kzg_b200_ctx *ctx);
+/* `verify_blob_kzg_proof_batch` over device-resident inputs.  Synchronous: 160 bytes per blob return to the host for
+ * the sequential hash of compute_r_powers and the final pairing check runs there.  All validations and all
+ * Fiat-Shamir challenges of the call run in one launch each. */
+int kzg_b200_verify_blob_kzg_proof_batch_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments,
+                                                const uint8_t *d_proofs, size_t n, int *ok);
 /*
  * Per-stage device timing of the calls on this context, measured with CUDA events on the
  * context's stream (bench.py's roofline numbers come from here).  enable(1) resets the

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkzg_b200.so")
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
-SOURCES = ["kzg_b200.cu", "msm.cu", "g1ops.cu", "frops.cu", "host_pairing.cpp"]
+SOURCES = ["kzg_b200.cu", "msm.cu", "g1ops.cu", "frops.cu", "host_pairing.cpp", "host_sha256.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
     "-lineinfo", "-Xcompiler", "-fPIC",

@@ -1,5 +1,7 @@
 // frops.cu -- launch functions of the scalar-field kernels (frpath.cuh): Fiat-Shamir challenges, barycentric
 // evaluation + quotient, and the r-power terms and sums of batch verification.
+#include <algorithm>
+
 #include "internal.h"
 #include "frpath.cuh"
 
@@ -36,10 +38,19 @@ int fr_launch_verify_terms(cudaStream_t st, const g1_affine_t *d_cpts, const g1_
     CU(cudaGetLastError());
     return KZG_B200_OK;
 }
+// sums[0] = sum V_i, sums[1] = sum (U1_i + U2_i) (affine), the scalar sum, and the 224-byte partial record.
+// d_partials: scratch for 2 * KZG_VERIFY_SUM_BLOCKS Jacobian points.
 int fr_launch_verify_sums(cudaStream_t st, const g1_jac_t *d_terms, const fr_t *d_sy, size_t count, g1_affine_t *d_sums,
-                          fr_t *d_sy_total, uint8_t *d_partial) {
-    k_jac_sum<<<2, KZG_JSUM_THREADS, 0, st>>>(d_terms, (uint32_t)count, d_sums);  // sums[0] = sum V_i, sums[1] = sum U_i
-    k_fr_sum<<<1, 256, 0, st>>>(d_sy, (uint32_t)count, d_sy_total);
+                          fr_t *d_sy_total, uint8_t *d_partial, g1_jac_t *d_partials) {
+    const uint32_t n = (uint32_t)count;
+    uint32_t per = (uint32_t)std::min<size_t>(KZG_VERIFY_SUM_BLOCKS, (2 * count + 4 * KZG_JSUM_THREADS - 1) / (4 * KZG_JSUM_THREADS));
+    if (per > 1) {
+        k_jac_sum_slices<<<2 * per, KZG_JSUM_THREADS, 0, st>>>(d_terms, n, 2 * n, per, d_partials);
+        k_jac_sum<<<2, KZG_JSUM_THREADS, 0, st>>>(d_partials, per, per, d_sums);
+    } else {
+        k_jac_sum<<<2, KZG_JSUM_THREADS, 0, st>>>(d_terms, n, 2 * n, d_sums);
+    }
+    k_fr_sum<<<1, 256, 0, st>>>(d_sy, n, d_sy_total);
     k_write_partial<<<1, 32, 0, st>>>(d_sums, d_sy_total, d_partial);
     CU(cudaGetLastError());
     return KZG_B200_OK;

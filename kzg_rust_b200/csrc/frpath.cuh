@@ -349,20 +349,17 @@ __global__ void __launch_bounds__(96) k_verify_terms(const g1_affine_t *__restri
     g1j_mul_glv(acc, base_pt, k.l);
     out_pts[role == 0 ? i : count + 2 * i + (role - 1)] = acc;
 }
-// Each block adds a run of Jacobian points -> out[block] (affine): strided partial
-// sums per thread, then a shared-memory tree.  The sums of batch verification are a few
-// thousand points at most, so one block each beats a log-depth chain of launches.
+// Sums of Jacobian points in two stages, so that a 16,384-blob batch (49,152 terms) is spread over the whole GPU:
+//   k_jac_sum_slices: segment 0 = pts[0, count0), segment 1 = pts[count0, count0 + count1); block b sums slice
+//                     b % per of segment b / per (strided partial sums per thread, then a shared-memory tree)
+//                     -> partials[b], Jacobian
+//   k_jac_sum:        block s sums pts[s ? count0 : 0, ...) of its segment -> out[s], affine
 #define KZG_JSUM_THREADS 128
-// block 0 sums pts[0, count), block 1 sums pts[count, 3 count)
-__global__ void __launch_bounds__(KZG_JSUM_THREADS) k_jac_sum(const g1_jac_t *__restrict__ pts, uint32_t count0,
-                                                              g1_affine_t *__restrict__ out) {
-    __shared__ g1_jac_t red[KZG_JSUM_THREADS];
-    const g1_jac_t *base = pts + (blockIdx.x ? count0 : 0);
-    const uint32_t count = blockIdx.x ? 2 * count0 : count0;
+KZG_D void jac_block_sum(g1_jac_t &total, const g1_jac_t *__restrict__ base, uint32_t lo, uint32_t hi, g1_jac_t *red) {
     g1_jac_t acc;
     g1j_set_inf(acc);
 #pragma unroll 1
-    for (uint32_t i = threadIdx.x; i < count; i += KZG_JSUM_THREADS) {
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += KZG_JSUM_THREADS) {
         g1_jac_t t = base[i];
         g1j_add(acc, acc, t);
     }
@@ -377,9 +374,26 @@ __global__ void __launch_bounds__(KZG_JSUM_THREADS) k_jac_sum(const g1_jac_t *__
         }
         __syncthreads();
     }
+    total = red[0];
+}
+__global__ void __launch_bounds__(KZG_JSUM_THREADS) k_jac_sum_slices(const g1_jac_t *__restrict__ pts, uint32_t count0, uint32_t count1,
+                                                                     uint32_t per, g1_jac_t *__restrict__ partials) {
+    __shared__ g1_jac_t red[KZG_JSUM_THREADS];
+    const uint32_t seg = blockIdx.x / per, j = blockIdx.x - seg * per;
+    const uint32_t cnt = seg ? count1 : count0;
+    const uint32_t lo = (uint32_t)((uint64_t)cnt * j / per), hi = (uint32_t)((uint64_t)cnt * (j + 1) / per);
+    g1_jac_t total;
+    jac_block_sum(total, pts + (seg ? count0 : 0), lo, hi, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(KZG_JSUM_THREADS) k_jac_sum(const g1_jac_t *__restrict__ pts, uint32_t count0, uint32_t count1,
+                                                              g1_affine_t *__restrict__ out) {
+    __shared__ g1_jac_t red[KZG_JSUM_THREADS];
+    g1_jac_t total;
+    jac_block_sum(total, pts + (blockIdx.x ? count0 : 0), 0, blockIdx.x ? count1 : count0, red);
     if (threadIdx.x == 0) {
         g1_affine_t a;
-        g1j_to_affine(a, red[0]);
+        g1j_to_affine(a, total);
         out[blockIdx.x] = a;
     }
 }

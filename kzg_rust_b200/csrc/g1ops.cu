@@ -24,6 +24,25 @@ int g1_launch_decode(cudaStream_t st, const uint8_t *d_in, g1_affine_t *d_out, i
     return KZG_B200_OK;
 }
 
+__global__ void k_decode_g1_pair(const uint8_t *in_a, const uint8_t *in_b, g1_affine_t *out_a, g1_affine_t *out_b, int32_t *status,
+                                 uint32_t count, int check_subgroup) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * count) return;
+    const bool second = t >= count;
+    const uint32_t i = second ? t - count : t;
+    g1_affine_t p;
+    int rc = g1_decode_thread(p, (second ? in_b : in_a) + 48ull * i, check_subgroup != 0);
+    (second ? out_b : out_a)[i] = p;
+    if (rc != KZG_OK && status) atomicMax(status + i, rc);
+}
+int g1_launch_decode2(cudaStream_t st, const uint8_t *d_commitments, const uint8_t *d_proofs, g1_affine_t *d_cpts, g1_affine_t *d_ppts,
+                      int32_t *d_status, size_t count, int check_subgroup) {
+    if (count == 0) return KZG_B200_OK;
+    k_decode_g1_pair<<<blocks_for(2 * count, 64), 64, 0, st>>>(d_commitments, d_proofs, d_cpts, d_ppts, d_status, (uint32_t)count, check_subgroup);
+    CU(cudaGetLastError());
+    return KZG_B200_OK;
+}
+
 // sums of blob i (W affine points at sums[j*stride + i]) -> Horner -> 48-byte compressed point
 __global__ void __launch_bounds__(64) k_horner_compress(const g1_affine_t *sums, size_t stride, int W, const int32_t *status,
                                                         uint8_t *out, uint32_t count) {

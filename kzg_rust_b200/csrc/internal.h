@@ -80,6 +80,9 @@ struct kzg_b200_ctx {
         uint8_t *d_zy = nullptr;           // chunk x 64 B: z || y big-endian
         kzg::g1_affine_t *d_pts = nullptr; // chunk x 2 decoded commitments / proofs
         cudaEvent_t ev_done = nullptr;
+        // point validation runs beside the challenge hash of the same chunk (both are latency-bound kernels)
+        cudaStream_t side_stream = nullptr;
+        cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr;
     };
     Lane lanes[2];
     int nlanes = 2;                   // KZG_B200_LANES
@@ -92,8 +95,6 @@ struct kzg_b200_ctx {
     uint8_t *d_stage_out = nullptr;   // slots x chunk x 96 B
     int32_t *d_status = nullptr;      // slots x chunk
     cudaStream_t copy_stream = nullptr;
-    cudaStream_t side_stream = nullptr;   // small verification calls: point validation beside the challenge hash
-    cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr;
     cudaEvent_t ev_h2d[KZG_SLOTS] = {nullptr, nullptr, nullptr}, ev_free[KZG_SLOTS] = {nullptr, nullptr, nullptr};
     host_g2_prepared *tau_prepared = nullptr;  // Miller-loop lines of [tau]G2
     kzg::g1_affine_t *d_sums_all = nullptr; // sums of a whole device-resident call, [bit position][blob] (grow-only)
@@ -137,6 +138,9 @@ void msm_free_lane(kzg_b200_ctx::Lane &ln);
 // status slot of point i is i % status_mod
 int g1_launch_decode(cudaStream_t st, const uint8_t *d_in, kzg::g1_affine_t *d_out, int32_t *d_status, size_t count,
                      int check_subgroup, size_t status_mod);
+// `count` commitments and `count` proofs in one launch; a bad commitment or proof of blob i marks status[i]
+int g1_launch_decode2(cudaStream_t st, const uint8_t *d_commitments, const uint8_t *d_proofs, kzg::g1_affine_t *d_cpts,
+                      kzg::g1_affine_t *d_ppts, int32_t *d_status, size_t count, int check_subgroup);
 // sums[j*stride + i], j < W  ->  48-byte compressed sum_j 2^j sums[j] of blob i (zeros where status[i] != 0)
 int g1_launch_horner_compress(cudaStream_t st, const kzg::g1_affine_t *d_sums, size_t stride, int W, const int32_t *d_status,
                               uint8_t *d_out, size_t count);
@@ -154,5 +158,6 @@ int fr_launch_eval(cudaStream_t st, int quotient, const uint8_t *d_blobs, const 
                    kzg::fr_t *d_inv, kzg::fr_t *d_poly, uint8_t *d_zy, int32_t *d_status, size_t count);
 int fr_launch_verify_terms(cudaStream_t st, const kzg::g1_affine_t *d_cpts, const kzg::g1_affine_t *d_ppts, const uint8_t *d_zy,
                            const kzg::fr_t &r_canon, uint64_t first, size_t count, kzg::g1_jac_t *d_terms, kzg::fr_t *d_sy);
+#define KZG_VERIFY_SUM_BLOCKS 148
 int fr_launch_verify_sums(cudaStream_t st, const kzg::g1_jac_t *d_terms, const kzg::fr_t *d_sy, size_t count,
-                          kzg::g1_affine_t *d_sums, kzg::fr_t *d_sy_total, uint8_t *d_partial);
+                          kzg::g1_affine_t *d_sums, kzg::fr_t *d_sy_total, uint8_t *d_partial, kzg::g1_jac_t *d_partials);

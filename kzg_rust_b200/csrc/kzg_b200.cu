@@ -126,14 +126,16 @@ static int ctx_init(kzg_b200_ctx *ctx, const uint8_t *g1_lagrange, size_t n1, co
     ctx->nlanes = env_int("KZG_B200_LANES", 2) >= 2 ? 2 : 1;
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&ctx->ev_side_fork, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&ctx->ev_side_join, cudaEventDisableTiming));
     ctx->lanes[0].stream = ctx->stream;
     CU(cudaStreamCreateWithFlags(&ctx->lanes[1].stream, cudaStreamNonBlocking));
     ctx->cur = &ctx->lanes[0];
     CU(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
-    for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&ctx->lanes[i].ev_done, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+        CU(cudaEventCreateWithFlags(&ctx->lanes[i].ev_done, cudaEventDisableTiming));
+        CU(cudaStreamCreateWithFlags(&ctx->lanes[i].side_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->lanes[i].ev_side_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->lanes[i].ev_side_join, cudaEventDisableTiming));
+    }
     for (int i = 0; i < KZG_SLOTS; i++) {
         CU(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
@@ -245,13 +247,15 @@ extern "C" void kzg_b200_ctx_destroy(kzg_b200_ctx *ctx) {
     cudaFree(ctx->d_roots);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
-    if (ctx->ev_side_fork) cudaEventDestroy(ctx->ev_side_fork);
-    if (ctx->ev_side_join) cudaEventDestroy(ctx->ev_side_join);
     if (ctx->lanes[1].stream) cudaStreamDestroy(ctx->lanes[1].stream);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
-    for (int i = 0; i < 2; i++)
-        if (ctx->lanes[i].ev_done) cudaEventDestroy(ctx->lanes[i].ev_done);
+    for (int i = 0; i < 2; i++) {
+        kzg_b200_ctx::Lane &ln = ctx->lanes[i];
+        if (ln.side_stream) { cudaStreamSynchronize(ln.side_stream); cudaStreamDestroy(ln.side_stream); }
+        if (ln.ev_done) cudaEventDestroy(ln.ev_done);
+        if (ln.ev_side_fork) cudaEventDestroy(ln.ev_side_fork);
+        if (ln.ev_side_join) cudaEventDestroy(ln.ev_side_join);
+    }
     for (int i = 0; i < KZG_SLOTS; i++) {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
         if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
@@ -490,5 +494,5 @@ extern "C" int kzg_b200_debug_check_tau_identity(kzg_b200_ctx *ctx, const uint8_
     return KZG_B200_OK;
 }
 
-#include "sha256.cuh"
+#include "host_sha256.h"
 #include "proof_verify.inl"

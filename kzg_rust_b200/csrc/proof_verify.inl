@@ -15,10 +15,11 @@ static int decode_points(kzg_b200_ctx *ctx, const uint8_t *d_bytes, g1_affine_t 
 // do not depend on the challenge hash that runs meanwhile.
 static int decode_points_side(kzg_b200_ctx *ctx, const uint8_t *d_bytes, g1_affine_t *d_out, int32_t *d_status, size_t count,
                               int check_subgroup, size_t status_mod) {
-    CU(cudaEventRecord(ctx->ev_side_fork, ctx->cur->stream));
-    CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side_fork, 0));
-    RC(g1_launch_decode(ctx->side_stream, d_bytes, d_out, d_status, count, check_subgroup, status_mod));
-    CU(cudaEventRecord(ctx->ev_side_join, ctx->side_stream));
+    kzg_b200_ctx::Lane *ln = ctx->cur;
+    CU(cudaEventRecord(ln->ev_side_fork, ln->stream));
+    CU(cudaStreamWaitEvent(ln->side_stream, ln->ev_side_fork, 0));
+    RC(g1_launch_decode(ln->side_stream, d_bytes, d_out, d_status, count, check_subgroup, status_mod));
+    CU(cudaEventRecord(ln->ev_side_join, ln->side_stream));
     ctx->launches++;
     return KZG_B200_OK;
 }
@@ -61,7 +62,7 @@ static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t 
     RC(msm_digits_from_scalars(ctx, ln->d_inv, count));  // the quotient, canonical, where the inverses were
     const g1_affine_t *res = nullptr;
     RC(msm_run(ctx, count, &res));
-    if (side) CU(cudaStreamWaitEvent(st, ctx->ev_side_join, 0));  // the compression reads the status the check wrote
+    if (side) CU(cudaStreamWaitEvent(st, ln->ev_side_join, 0));  // the compression reads the status the check wrote
     return compress_or_park(ctx, res, off, count, d_status, d_proofs, dc);
 }
 
@@ -161,11 +162,79 @@ extern "C" int kzg_b200_compute_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t
 }
 
 // ------------------------------------------------------------------ verify_blob_kzg_proof_batch
-// Phase A (reference src/kzg.rs:671-683, per blob): validate C_i and proof_i, z_i, y_i.
+// Device buffers of one verification call (grow-only, kept by the context): the decoded points and the (z, y)
+// records of the WHOLE call, so that phase B reads what phase A left on the device, plus phase B's own workspace.
+struct VerifyBufs {
+    g1_affine_t *pts;      // 2n: commitments, then proofs
+    uint8_t *zy;           // n x 64
+    uint8_t *in_bytes;     // 96 n: commitment and proof bytes when they have to be uploaded for phase B
+    int32_t *status;       // 2n
+    g1_jac_t *terms;       // 3n
+    g1_jac_t *partials;    // 2 x KZG_VERIFY_SUM_BLOCKS
+    g1_affine_t *sums;     // 2
+    fr_t *sy;              // n + 1
+    uint8_t *partial;      // 256
+};
+static int verify_bufs(kzg_b200_ctx *ctx, size_t n, VerifyBufs *vb) {
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t o_pts = 0, o_zy = o_pts + up(2 * n * sizeof(g1_affine_t)), o_in = o_zy + up(64 * n), o_st = o_in + up(96 * n),
+                 o_terms = o_st + up(2 * n * sizeof(int32_t)), o_partials = o_terms + up(3 * n * sizeof(g1_jac_t)),
+                 o_sums = o_partials + up(2 * KZG_VERIFY_SUM_BLOCKS * sizeof(g1_jac_t)), o_sy = o_sums + up(2 * sizeof(g1_affine_t)),
+                 o_part = o_sy + up((n + 1) * sizeof(fr_t)), total = o_part + 256;
+    if (total > ctx->vb_bytes) {
+        if (ctx->d_vb) CU(cudaFree(ctx->d_vb));
+        ctx->d_vb = nullptr;
+        ctx->vb_bytes = 0;
+        CU(cudaMalloc(&ctx->d_vb, total + total / 2));
+        ctx->vb_bytes = total + total / 2;
+    }
+    uint8_t *d = ctx->d_vb;
+    vb->pts = (g1_affine_t *)(d + o_pts); vb->zy = d + o_zy; vb->in_bytes = d + o_in; vb->status = (int32_t *)(d + o_st);
+    vb->terms = (g1_jac_t *)(d + o_terms); vb->partials = (g1_jac_t *)(d + o_partials); vb->sums = (g1_affine_t *)(d + o_sums);
+    vb->sy = (fr_t *)(d + o_sy); vb->partial = d + o_part;
+    return KZG_B200_OK;
+}
+
+// Phase A of one chunk on the current lane (reference src/kzg.rs:671-683, per blob): validate C_i and proof_i
+// (beside the hash, on the lane's side stream), z_i, y_i.  d_cp: cnt commitments then cnt proofs, 48 B each.
+// The decoded points go to pts[off + i] (commitments) and pts[n_total + off + i] (proofs), (z, y) to zy[off + i].
+static int verify_chunk_a(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments, const uint8_t *d_proofs, size_t cnt,
+                          size_t off, size_t n_total, const VerifyBufs &vb, int32_t *d_st) {
+    kzg_b200_ctx::Lane *ln = ctx->cur;
+    cudaStream_t sm = ln->stream;
+    CU(cudaMemsetAsync(d_st, 0, cnt * sizeof(int32_t), sm));
+    const bool side = !ctx->profile;  // profiling keeps the stages apart
+    cudaStream_t sd = side ? ln->side_stream : sm;
+    if (side) {
+        CU(cudaEventRecord(ln->ev_side_fork, sm));
+        CU(cudaStreamWaitEvent(sd, ln->ev_side_fork, 0));
+    }
+    stage_begin(ctx, KZG_B200_STAGE_VALIDATE);
+    int rc = g1_launch_decode2(sd, d_commitments, d_proofs, vb.pts + off, vb.pts + n_total + off, d_st, cnt, 1);
+    stage_end(ctx, 1);
+    RC(rc);
+    if (side) CU(cudaEventRecord(ln->ev_side_join, sd));
+    stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
+    rc = fr_launch_challenge(sm, d_blobs, d_commitments, cnt, ctx->n, ln->d_z);
+    stage_end(ctx, 1);
+    RC(rc);
+    stage_begin(ctx, KZG_B200_STAGE_EVAL);
+    rc = fr_launch_eval(sm, 0, d_blobs, ln->d_z, ctx->d_roots, ctx->n, ln->d_inv, ln->d_poly, vb.zy + 64 * off, d_st, cnt);
+    stage_end(ctx, 1);
+    ctx->launches += 3;
+    RC(rc);
+    if (side) CU(cudaStreamWaitEvent(sm, ln->ev_side_join, 0));
+    return KZG_B200_OK;
+}
+
+// Phase A over host buffers: chunks staged through the upload slots, two chunks in flight.
+// keep != nullptr: the decoded points and (z, y) records stay in the call's device buffers for phase B.
 static int verify_phase_a_locked(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments, const uint8_t *proofs,
-                                 size_t n, uint8_t *zy_out) {
+                                 size_t n, uint8_t *zy_out, VerifyBufs *keep = nullptr) {
     const size_t bpb = (size_t)ctx->n * 32, ch = ctx->chunk;
-    const size_t nchunks_total = (n + ch - 1) / ch;
+    VerifyBufs vb;
+    RC(verify_bufs(ctx, n, &vb));
+    if (keep) *keep = vb;
     std::vector<int32_t> st(n);
     RC(staged_chunks(
         ctx, n,
@@ -179,24 +248,9 @@ static int verify_phase_a_locked(kzg_b200_ctx *ctx, const uint8_t *blobs, const 
         [&](int slot, size_t off, size_t cnt) -> int {
             const uint8_t *d_blobs = ctx->d_stage_in + slot * ch * bpb, *aux = ctx->d_stage_aux + slot * ch * 96;
             int32_t *d_st = ctx->d_status + slot * ch;
-            kzg_b200_ctx::Lane *ln = ctx->cur;
-            cudaStream_t sm = ln->stream;
-            CU(cudaMemsetAsync(d_st, 0, cnt * sizeof(int32_t), sm));
-            // single-chunk calls validate the points beside the hash (profiling keeps the stages apart)
-            const bool side = nchunks_total == 1 && !ctx->profile;
-            if (side) RC(decode_points_side(ctx, aux, ln->d_pts, d_st, 2 * cnt, 1, cnt));
-            else RC(decode_points(ctx, aux, ln->d_pts, d_st, 2 * cnt, 1, cnt));
-            stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
-            int rc = fr_launch_challenge(sm, d_blobs, aux, cnt, ctx->n, ln->d_z);
-            stage_end(ctx, 1);
-            RC(rc);
-            stage_begin(ctx, KZG_B200_STAGE_EVAL);
-            rc = fr_launch_eval(sm, 0, d_blobs, ln->d_z, ctx->d_roots, ctx->n, ln->d_inv, ln->d_poly, ln->d_zy, d_st, cnt);
-            stage_end(ctx, 1);
-            ctx->launches += 2;
-            RC(rc);
-            if (side) CU(cudaStreamWaitEvent(sm, ctx->ev_side_join, 0));
-            CU(cudaMemcpyAsync(zy_out + off * 64, ln->d_zy, cnt * 64, cudaMemcpyDeviceToHost, sm));
+            RC(verify_chunk_a(ctx, d_blobs, aux, aux + cnt * 48, cnt, off, n, vb, d_st));
+            cudaStream_t sm = ctx->cur->stream;
+            CU(cudaMemcpyAsync(zy_out + off * 64, vb.zy + 64 * off, cnt * 64, cudaMemcpyDeviceToHost, sm));
             CU(cudaMemcpyAsync(st.data() + off, d_st, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, sm));
             return KZG_B200_OK;
         }));
@@ -217,7 +271,7 @@ extern "C" int kzg_b200_verify_phase_a(kzg_b200_ctx *ctx, const uint8_t *blobs, 
 extern "C" int kzg_b200_compute_r(const kzg_b200_ctx *ctx, const uint8_t *commitments, const uint8_t *zy,
                                   const uint8_t *proofs, size_t n_total, uint8_t r_out[32]) {
     if (!ctx || !r_out || (n_total && (!commitments || !zy || !proofs))) return KZG_B200_BAD_ARGS;
-    Sha256 h;
+    HostSha256 h;
     h.init();
     h.update((const uint8_t *)"RCKZGBATCH___V1_", 16);
     uint8_t u[8];
@@ -239,61 +293,56 @@ extern "C" int kzg_b200_compute_r(const kzg_b200_ctx *ctx, const uint8_t *commit
     return KZG_B200_OK;
 }
 
-// Phase B: the r-power linear combinations of one shard (reference src/kzg.rs:601-622).
-// d_pts_ready (optional): the 2n points phase A decoded on this context (commitments, then proofs)
-static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, const uint8_t *zy, const uint8_t *proofs,
-                                 size_t n, const uint8_t r[32], uint64_t first_index, uint8_t partial_out[224],
-                                 const g1_affine_t *d_pts_ready = nullptr, int check_subgroup = 0) {
-    if (n == 0) {
-        memset(partial_out, 0, 224);
-        partial_out[0] = 0x40;
-        partial_out[96] = 0x40;
-        return KZG_B200_OK;
-    }
+// Phase B on the device: the r-power linear combinations of one shard (reference src/kzg.rs:601-622) from
+// decoded, validated points vb.pts (n commitments at [0, n), n proofs at [n_stride, n_stride + n)) and vb.zy.
+static int verify_phase_b_device(kzg_b200_ctx *ctx, const VerifyBufs &vb, size_t n, size_t n_stride, const uint8_t r[32],
+                                 uint64_t first_index, uint8_t partial_out[224]) {
     fr_t rc;
     scalar_from_be32(rc, r);
     if (!fr_is_canonical(rc)) return KZG_B200_BAD_ARGS;
     ctx->cur = &ctx->lanes[0];
-    // one buffer: bytes (48 + 48 + 64) n | status 2n | points 2n | terms 3n (Jacobian) | sums 2 | sy n + 1 | partial
-    const size_t o_c = 0, o_p = o_c + 48 * n, o_zy = o_p + 48 * n;
-    size_t o_st = (o_zy + 64 * n + 15) / 16 * 16;
-    size_t o_pts = (o_st + 2 * n * sizeof(int32_t) + 15) / 16 * 16;
-    size_t o_terms = o_pts + 2 * n * sizeof(g1_affine_t);
-    size_t o_sums = o_terms + 3 * n * sizeof(g1_jac_t);
-    size_t o_sy = o_sums + 2 * sizeof(g1_affine_t);
-    size_t o_part = o_sy + (n + 1) * sizeof(fr_t);
-    size_t total = o_part + 256;
-    if (total > ctx->vb_bytes) {  // grow-only buffer kept by the context
-        if (ctx->d_vb) CU(cudaFree(ctx->d_vb));
-        ctx->d_vb = nullptr;
-        ctx->vb_bytes = 0;
-        CU(cudaMalloc(&ctx->d_vb, total + total / 2));
-        ctx->vb_bytes = total + total / 2;
-    }
-    uint8_t *d = ctx->d_vb;
-    CU(cudaMemcpyAsync(d + o_c, commitments, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(d + o_p, proofs, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(d + o_zy, zy, 64 * n, cudaMemcpyHostToDevice, ctx->stream));
-    int32_t *d_st = (int32_t *)(d + o_st);
-    g1_affine_t *pts = (g1_affine_t *)(d + o_pts), *sums = (g1_affine_t *)(d + o_sums);
-    g1_jac_t *terms = (g1_jac_t *)(d + o_terms);
-    fr_t *sy = (fr_t *)(d + o_sy);
-    CU(cudaMemsetAsync(d_st, 0, 2 * n * sizeof(int32_t), ctx->stream));
-    // c and p byte arrays are contiguous: decode both with one launch (phase A did the subgroup checks)
-    if (d_pts_ready) CU(cudaMemcpyAsync(pts, d_pts_ready, 2 * n * sizeof(g1_affine_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    else RC(decode_points(ctx, d + o_c, pts, d_st, 2 * n, check_subgroup, 2 * n));
     stage_begin(ctx, KZG_B200_STAGE_VERIFY_TERMS);
-    int lrc = fr_launch_verify_terms(ctx->stream, pts, pts + n, d + o_zy, rc, first_index, n, terms, sy);
-    if (lrc == KZG_B200_OK) lrc = fr_launch_verify_sums(ctx->stream, terms, sy, n, sums, sy + n, d + o_part);
-    stage_end(ctx, 4);
-    ctx->launches += 4;
+    int lrc = fr_launch_verify_terms(ctx->stream, vb.pts, vb.pts + n_stride, vb.zy, rc, first_index, n, vb.terms, vb.sy);
+    if (lrc == KZG_B200_OK) lrc = fr_launch_verify_sums(ctx->stream, vb.terms, vb.sy, n, vb.sums, vb.sy + n, vb.partial, vb.partials);
+    stage_end(ctx, 5);
+    ctx->launches += 5;
     RC(lrc);
-    std::vector<int32_t> st(2 * n);
-    CU(cudaMemcpyAsync(st.data(), d_st, 2 * n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(partial_out, d + o_part, 224, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(partial_out, vb.partial, 224, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     stage_collect(ctx);
-    for (size_t i = 0; i < 2 * n; i++)
+    return KZG_B200_OK;
+}
+static void empty_partial(uint8_t partial_out[224]) {
+    memset(partial_out, 0, 224);
+    partial_out[0] = 0x40;
+    partial_out[96] = 0x40;
+}
+// Phase B from host bytes: nothing is assumed about them -- the points are decompressed AND subgroup-checked here,
+// z_i and y_i must be canonical (a caller may run phase B on another context, or on re-fetched data, than phase A).
+static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, const uint8_t *zy, const uint8_t *proofs,
+                                 size_t n, const uint8_t r[32], uint64_t first_index, uint8_t partial_out[224]) {
+    if (n == 0) { empty_partial(partial_out); return KZG_B200_OK; }
+    for (size_t i = 0; i < 2 * n; i++) {
+        fr_t t;
+        scalar_from_be32(t, zy + 32 * i);
+        if (!fr_is_canonical(t)) return KZG_B200_BAD_ARGS;  // bytes_to_bls_field, src/utils.rs:262-275
+    }
+    VerifyBufs vb;
+    RC(verify_bufs(ctx, n, &vb));
+    ctx->cur = &ctx->lanes[0];
+    CU(cudaMemcpyAsync(vb.in_bytes, commitments, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(vb.in_bytes + 48 * n, proofs, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(vb.zy, zy, 64 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(vb.status, 0, n * sizeof(int32_t), ctx->stream));
+    stage_begin(ctx, KZG_B200_STAGE_VALIDATE);
+    int rc = g1_launch_decode2(ctx->stream, vb.in_bytes, vb.in_bytes + 48 * n, vb.pts, vb.pts + n, vb.status, n, 1);
+    stage_end(ctx, 1);
+    ctx->launches++;
+    RC(rc);
+    std::vector<int32_t> st(n);
+    CU(cudaMemcpyAsync(st.data(), vb.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    RC(verify_phase_b_device(ctx, vb, n, n, r, first_index, partial_out));
+    for (size_t i = 0; i < n; i++)
         if (st[i] != KZG_B200_OK) return KZG_B200_BAD_ARGS;
     return KZG_B200_OK;
 }
@@ -322,34 +371,92 @@ extern "C" int kzg_b200_verify_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const uin
     // (src/kzg.rs:658-660 -> :409-426); for points of G1 it holds exactly when the batch equation
     // with r^0 = 1 does, so the same path serves both.
     std::vector<uint8_t> zy(n * 64);
-    RC(verify_phase_a_locked(ctx, blobs, commitments, proofs, n, zy.data()));
+    VerifyBufs vb;
+    RC(verify_phase_a_locked(ctx, blobs, commitments, proofs, n, zy.data(), &vb));
     uint8_t r[32], partial[224];
     RC(kzg_b200_compute_r(ctx, commitments, zy.data(), proofs, n, r));
-    // a single-chunk call still has phase A's decoded points in lane 0's workspace
-    RC(verify_phase_b_locked(ctx, commitments, zy.data(), proofs, n, r, 0, partial, n <= ctx->chunk ? ctx->lanes[0].d_pts : nullptr));
+    // phase A left the decoded points and the (z, y) records of the whole call on the device
+    RC(verify_phase_b_device(ctx, vb, n, n, r, 0, partial));
+    return host_verify_finish(partial, 1, ctx->tau_prepared, ok) == 0 ? KZG_B200_OK : KZG_B200_BAD_ARGS;
+}
+
+// The same for blobs, commitments and proofs that are already in this context's GPU memory (16-byte aligned).
+// Every validation and every Fiat-Shamir challenge of the call runs in ONE launch each (per chunk they are
+// latency-bound: one SHA-256 stream per blob), the evaluations chunk by chunk; 160 bytes per blob come back to
+// the host for the sequential hash of compute_r_powers, and the final pairing check runs on the host.  Synchronous.
+extern "C" int kzg_b200_verify_blob_kzg_proof_batch_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments,
+                                                           const uint8_t *d_proofs, size_t n, int *ok) {
+    if (!ctx || !ok || (n && (!d_blobs || !d_commitments || !d_proofs))) return KZG_B200_BAD_ARGS;
+    if (!aligned16(d_blobs) || !aligned16(d_commitments) || !aligned16(d_proofs)) return KZG_B200_BAD_ARGS;
+    *ok = 0;
+    if (n == 0) { *ok = 1; return KZG_B200_OK; }
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const size_t bpb = (size_t)ctx->n * 32;
+    VerifyBufs vb;
+    RC(verify_bufs(ctx, n, &vb));
+    if (n > ctx->z_all_elems) {
+        if (ctx->d_z_all) CU(cudaFree(ctx->d_z_all));
+        ctx->d_z_all = nullptr;
+        ctx->z_all_elems = 0;
+        CU(cudaMalloc(&ctx->d_z_all, n * (sizeof(fr_t) + sizeof(g1_affine_t))));
+        ctx->z_all_elems = n;
+    }
+    kzg_b200_ctx::Lane *ln = ctx->cur = &ctx->lanes[0];
+    cudaStream_t sm = ctx->stream, sd = ctx->profile ? sm : ln->side_stream;
+    CU(cudaMemsetAsync(vb.status, 0, n * sizeof(int32_t), sm));
+    CU(cudaEventRecord(ln->ev_side_fork, sm));
+    CU(cudaStreamWaitEvent(sd, ln->ev_side_fork, 0));
+    stage_begin(ctx, KZG_B200_STAGE_VALIDATE);
+    int rc = g1_launch_decode2(sd, d_commitments, d_proofs, vb.pts, vb.pts + n, vb.status, n, 1);
+    stage_end(ctx, 1);
+    RC(rc);
+    CU(cudaEventRecord(ln->ev_side_join, sd));
+    stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
+    rc = fr_launch_challenge(sm, d_blobs, d_commitments, n, ctx->n, ctx->d_z_all);
+    stage_end(ctx, 1);
+    RC(rc);
+    ctx->launches += 2;
+    stage_begin(ctx, KZG_B200_STAGE_EVAL);
+    uint64_t evals = 0;
+    for (size_t off = 0; off < n; off += ctx->chunk, evals++) {
+        const size_t cnt = std::min(ctx->chunk, n - off);
+        RC(fr_launch_eval(sm, 0, d_blobs + off * bpb, ctx->d_z_all + off, ctx->d_roots, ctx->n, ln->d_inv, ln->d_poly, vb.zy + 64 * off,
+                          vb.status + off, cnt));
+    }
+    stage_end(ctx, evals);
+    ctx->launches += evals;
+    CU(cudaStreamWaitEvent(sm, ln->ev_side_join, 0));
+    std::vector<uint8_t> zy(n * 64), cm(n * 48), pr(n * 48);
+    std::vector<int32_t> st(n);
+    CU(cudaMemcpyAsync(zy.data(), vb.zy, n * 64, cudaMemcpyDeviceToHost, sm));
+    CU(cudaMemcpyAsync(cm.data(), d_commitments, n * 48, cudaMemcpyDeviceToHost, sm));
+    CU(cudaMemcpyAsync(pr.data(), d_proofs, n * 48, cudaMemcpyDeviceToHost, sm));
+    CU(cudaMemcpyAsync(st.data(), vb.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, sm));
+    CU(cudaStreamSynchronize(sm));
+    for (size_t i = 0; i < n; i++)
+        if (st[i] != KZG_B200_OK) return KZG_B200_BAD_ARGS;
+    uint8_t r[32], partial[224];
+    RC(kzg_b200_compute_r(ctx, cm.data(), zy.data(), pr.data(), n, r));
+    RC(verify_phase_b_device(ctx, vb, n, n, r, 0, partial));
     return host_verify_finish(partial, 1, ctx->tau_prepared, ok) == 0 ? KZG_B200_OK : KZG_B200_BAD_ARGS;
 }
 
 // reference verify_kzg_proof (src/kzg.rs:429-445 -> verify_kzg_proof_impl :409-426): no blob, the caller gives
 // z and the claimed y.  e(C - [y]G, G2) == e(proof, [tau - z]G2) is, for points of G1, the batch equation with
-// one term and r^0 = 1 -- e(proof, [tau]G2) == e(C - [y]G + [z]proof, G2) -- so phase B and the final check are
-// reused; here the points get their subgroup check in phase B because there is no phase A.
+// one term and r^0 = 1 -- e(proof, [tau]G2) == e(C - [y]G + [z]proof, G2) -- so phase B (which validates the points
+// and the scalars) and the final check are reused.
 extern "C" int kzg_b200_verify_kzg_proof(kzg_b200_ctx *ctx, const uint8_t commitment[48], const uint8_t z[32],
                                          const uint8_t y[32], const uint8_t proof[48], int *ok) {
     if (!ctx || !commitment || !z || !y || !proof || !ok) return KZG_B200_BAD_ARGS;
     *ok = 0;
-    fr_t t;
-    scalar_from_be32(t, z);
-    if (!fr_is_canonical(t)) return KZG_B200_BAD_ARGS;  // bytes_to_bls_field, src/utils.rs:262-275
-    scalar_from_be32(t, y);
-    if (!fr_is_canonical(t)) return KZG_B200_BAD_ARGS;
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     uint8_t zy[64], one[32] = {0}, partial[224];
     memcpy(zy, z, 32);
     memcpy(zy + 32, y, 32);
     one[31] = 1;
-    RC(verify_phase_b_locked(ctx, commitment, zy, proof, 1, one, 0, partial, nullptr, 1));
+    RC(verify_phase_b_locked(ctx, commitment, zy, proof, 1, one, 0, partial));
     return host_verify_finish(partial, 1, ctx->tau_prepared, ok) == 0 ? KZG_B200_OK : KZG_B200_BAD_ARGS;
 }
 

@@ -7,10 +7,10 @@ challenge r hashes every blob's (C_i, z_i, y_i, proof_i) (compute_r_powers,
 src/utils.rs:426-474):
 
     phase A (local)   validate, z_i, y_i                           kzg_b200_verify_phase_a
-    exchange 1        all_gather of the 160-byte records
+    exchange 1        ONE all_gather: status + 160-byte records (C_i, z_i, y_i, proof_i)
     r                 one sequential SHA-256 over all records      kzg_b200_compute_r
     phase B (local)   partial sums with r^(first + i)              kzg_b200_verify_phase_b
-    exchange 2        all_gather of one 224-byte partial per rank
+    exchange 2        ONE all_gather: status + one 224-byte partial per rank
     finish            add the partials, one pairing check (host)   kzg_b200_verify_finish
 
 The payloads are a few hundred bytes per rank, so the collective is plain
@@ -82,14 +82,17 @@ def _all_gather_bytes(local, sizes, device):
     buf = buf.to(device)
     outs = [torch.empty(width, dtype=torch.uint8, device=device) for _ in sizes]
     dist.all_gather(outs, buf)
-    return np.concatenate([o.cpu().numpy()[:sz] for o, sz in zip(outs, sizes)]) if sizes else np.zeros(0, np.uint8)
+    return [o.cpu().numpy()[:sz] for o, sz in zip(outs, sizes)] if sizes else []
 
 
 def verify_blob_kzg_proof_batch_sharded(backend, blobs, commitments, proofs, n_total, device="cpu"):
     """Every rank passes ITS contiguous shard (shard_range(n_total, rank, world)) and gets the
     verdict for the whole batch.  Raises BadArgs on every rank if any shard holds a malformed blob,
-    commitment or proof (the reference's first-error abort, src/kzg.rs:671-683, seen from outside)."""
-    import torch
+    commitment or proof (the reference's first-error abort, src/kzg.rs:671-683, seen from outside).
+
+    Two collectives per verdict: one all_gather of the shards' records (status byte + 160 B per blob: C_i, z_i,
+    y_i, proof_i -- exactly what compute_r_powers hashes, so every rank derives the same r without a broadcast),
+    and one all_gather of the 224-byte partial sums (+ status byte)."""
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
@@ -102,25 +105,33 @@ def verify_blob_kzg_proof_batch_sharded(backend, blobs, commitments, proofs, n_t
         return True
     rc, zy = backend.phase_a(blobs, commitments, proofs) if n_local else (0, np.zeros(0, np.uint8))
     if world > 1:
-        flag = torch.tensor([rc], dtype=torch.int32, device=device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        rc = int(flag.item())
-    if rc:
-        _k._raise(rc, "verify_blob_kzg_proof_batch (phase A)")
-    if world > 1:
         counts = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
-        all_c = _all_gather_bytes(commitments, [48 * c for c in counts], device)
-        all_p = _all_gather_bytes(proofs, [48 * c for c in counts], device)
-        all_zy = _all_gather_bytes(zy, [64 * c for c in counts], device)
+        rec = np.zeros(1 + 160 * n_local, dtype=np.uint8)
+        rec[0] = min(rc, 255)
+        if n_local and not rc:
+            body = rec[1:].reshape(n_local, 160)
+            body[:, :48] = commitments.reshape(n_local, 48)
+            body[:, 48:112] = zy.reshape(n_local, 64)
+            body[:, 112:] = proofs.reshape(n_local, 48)
+        recs = _all_gather_bytes(rec, [1 + 160 * c for c in counts], device)
+        rc = max(int(r[0]) for r in recs)
+        if rc:
+            _k._raise(rc, "verify_blob_kzg_proof_batch (phase A)")
+        body = np.concatenate([r[1:] for r in recs]).reshape(n_total, 160)
+        all_c = np.ascontiguousarray(body[:, :48]).reshape(-1)
+        all_zy = np.ascontiguousarray(body[:, 48:112]).reshape(-1)
+        all_p = np.ascontiguousarray(body[:, 112:]).reshape(-1)
     else:
+        if rc:
+            _k._raise(rc, "verify_blob_kzg_proof_batch (phase A)")
         all_c, all_p, all_zy = commitments, proofs, zy
     r = backend.compute_r(all_c, all_zy, all_p)       # every rank hashes the same bytes: no broadcast needed
     rc, part = backend.phase_b(commitments, zy, proofs, r, lo)
     if world > 1:
-        flag = torch.tensor([rc], dtype=torch.int32, device=device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        rc = int(flag.item())
-        parts = _all_gather_bytes(part, [224] * world, device)
+        rec = np.concatenate([np.array([min(rc, 255)], dtype=np.uint8), part])
+        recs = _all_gather_bytes(rec, [225] * world, device)
+        rc = max(int(x[0]) for x in recs)
+        parts = np.concatenate([x[1:] for x in recs])
     else:
         parts = part
     if rc:

@@ -10,7 +10,7 @@ use std::env;
 use std::path::PathBuf;
 use std::process::Command;
 
-const SOURCES: [&str; 5] = ["kzg_b200.cu", "msm.cu", "g1ops.cu", "frops.cu", "host_pairing.cpp"];
+const SOURCES: [&str; 6] = ["kzg_b200.cu", "msm.cu", "g1ops.cu", "frops.cu", "host_pairing.cpp", "host_sha256.cpp"];
 const NVCC_FLAGS: [&str; 9] = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",

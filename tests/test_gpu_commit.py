@@ -168,7 +168,7 @@ def test_load_trusted_setup_file(tmp_path):
     with pytest.raises(k.InvalidTrustedSetup):
         k.Kzg.load_trusted_setup_file(str(tmp_path / "missing.txt"), 0, 6)
     bad = tmp_path / "not_a_point.txt"
-    bad.write_text("\n".join(text[:2] + ["8" + "0" * 94 + "05"] + text[3:]))  # x = 5: x^3 + 4 is not a square
+    bad.write_text("\n".join(text[:2] + ["8" + "0" * 94 + "07"] + text[3:]))  # x = 7: x^3 + 4 is not a square
     with pytest.raises(k.Error):
         k.Kzg.load_trusted_setup_file(str(bad), 0, 6)
 

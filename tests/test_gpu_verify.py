@@ -220,3 +220,132 @@ def test_verify_kzg_proof_vectors(case, width):
         assert case["output"] is None
         return
     assert ok is case["output"]
+
+
+def test_device_resident_verification_and_multi_chunk_host_calls():
+    """kzg_b200_verify_blob_kzg_proof_batch_device (whole-call validation and challenges) and the host-buffer call
+    over several chunks on two lanes agree: true for a good batch, false after a swap, BadArgs for a point off the
+    curve / outside G1 and for a non-canonical blob element."""
+    import torch
+    k = _kzg()
+    L = k.load_library()
+    os.environ["KZG_B200_CHUNK"] = "24"
+    try:
+        s = k.KzgSettings.load_trusted_setup(G.g1_bytes, G.g2_bytes, 0, 7)
+    finally:
+        del os.environ["KZG_B200_CHUNK"]
+    n = 100  # 5 chunks of 24
+    blobs, cms, proofs = _make_batch(k, s, n, 4242)
+    dev = torch.device("cuda", 0)
+    d_b, d_c = torch.from_numpy(blobs).to(dev), torch.from_numpy(cms).to(dev)
+
+    def device_verify(pr, bl=d_b, cm=d_c):
+        d_p = torch.from_numpy(pr).to(dev)
+        ok = ctypes.c_int(-1)
+        rc = L.kzg_b200_verify_blob_kzg_proof_batch_device(s._h, bl.data_ptr(), cm.data_ptr(), d_p.data_ptr(), n, ctypes.byref(ok))
+        return rc, bool(ok.value)
+
+    assert device_verify(proofs) == (0, True)
+    assert k.Kzg.verify_blob_kzg_proof_batch_raw(blobs, cms, proofs, n, s) is True
+    bad = proofs.copy()
+    bad[[3, 77]] = bad[[77, 3]]
+    assert device_verify(bad) == (0, False)
+    assert k.Kzg.verify_blob_kzg_proof_batch_raw(blobs, cms, bad, n, s) is False
+    from oracle.binding import validate_kzg_g1
+    bad = proofs.copy()
+    bad[60, 47] ^= 1
+    if not validate_kzg_g1(bad[60].tobytes()):
+        assert device_verify(bad)[0] == 1
+        with pytest.raises(k.BadArgs):
+            k.Kzg.verify_blob_kzg_proof_batch_raw(blobs, cms, bad, n, s)
+    b2 = blobs.copy()
+    b2[90, :32] = 0xff  # element >= r
+    assert device_verify(proofs, bl=torch.from_numpy(b2).to(dev))[0] == 1
+    with pytest.raises(k.BadArgs):
+        k.Kzg.verify_blob_kzg_proof_batch_raw(b2, cms, proofs, n, s)
+    # unaligned device pointers are refused, not faulted on
+    ok = ctypes.c_int(-1)
+    d_p = torch.from_numpy(proofs).to(dev)
+    assert L.kzg_b200_verify_blob_kzg_proof_batch_device(s._h, d_b.data_ptr() + 4, d_c.data_ptr(), d_p.data_ptr(), n - 1, ctypes.byref(ok)) == 1
+    s.close()
+
+
+def test_phase_b_validates_what_it_is_given():
+    """Phase B may run on another context, or on other data, than phase A: it subgroup-checks the points and range-checks
+    z and y itself (a point of the curve outside G1 must not reach the ladders)."""
+    k = _kzg()
+    L = k.load_library()
+    s = gpu_settings("mainnet", 8)
+    n = 3
+    blobs, cms, proofs = _make_batch(k, s, n, 99)
+    zy = np.zeros((n, 64), dtype=np.uint8)
+    assert L.kzg_b200_verify_phase_a(s._h, blobs.ctypes.data, cms.ctypes.data, proofs.ctypes.data, n, zy.ctypes.data) == 0
+    r = np.zeros(32, dtype=np.uint8)
+    assert L.kzg_b200_compute_r(s._h, cms.ctypes.data, zy.ctypes.data, proofs.ctypes.data, n, r.ctypes.data) == 0
+    part = np.zeros(224, dtype=np.uint8)
+    call = lambda c, z, p: L.kzg_b200_verify_phase_b(s._h, c.ctypes.data, z.ctypes.data, p.ctypes.data, n, r.ctypes.data, 0, part.ctypes.data)
+    assert call(cms, zy, proofs) == 0
+    # a point on the curve but not in G1: any x with x^3 + 4 a square (the cofactor is ~2^125)
+    P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    from oracle.binding import validate_kzg_g1
+    x = 5
+    while True:
+        rhs = (x ** 3 + 4) % P
+        y = pow(rhs, (P + 1) // 4, P)
+        if y * y % P == rhs:
+            enc = bytearray(x.to_bytes(48, "big"))
+            enc[0] |= 0x80 | (0x20 if y > (P - 1) // 2 else 0)
+            if not validate_kzg_g1(bytes(enc)):
+                break
+        x += 1
+    bad_point = np.frombuffer(bytes(enc), dtype=np.uint8)
+    # ... which decompresses fine: with the subgroup check off it would be accepted as an operand
+    pr = proofs.copy()
+    pr[1] = bad_point
+    assert call(cms, zy, pr) == 1
+    cm = cms.copy()
+    cm[2] = bad_point
+    assert call(cm, zy, proofs) == 1
+    z2 = zy.copy()
+    z2[0, :32] = 0xff
+    assert call(cms, z2, proofs) == 1
+    z2 = zy.copy()
+    z2[2, 32:] = np.frombuffer(R.to_bytes(32, "big"), dtype=np.uint8)
+    assert call(cms, z2, proofs) == 1
+
+
+def test_one_context_from_several_host_threads():
+    """The reference API is re-entrant and `&KzgSettings` is shareable: commitments, proofs and
+    verifications issued concurrently from four host threads on one context give the serial results."""
+    import threading
+    k = _kzg()
+    s = gpu_settings("mainnet", 8)
+    sets = [_make_batch(k, s, 5 + t, 500 + t) for t in range(4)]
+    results, errors = [None] * 4, []
+
+    def work(t):
+        try:
+            blobs, cms, proofs = sets[t]
+            out = []
+            for _ in range(3):
+                c, st = k.Kzg.blob_to_kzg_commitment_batch(blobs, s)
+                p, st2 = k.Kzg.compute_blob_kzg_proof_batch(blobs, c, s)
+                ok = k.Kzg.verify_blob_kzg_proof_batch_raw(blobs, c, p, len(c), s)
+                bad = p.copy()
+                bad[[0, 1]] = bad[[1, 0]]
+                nok = k.Kzg.verify_blob_kzg_proof_batch_raw(blobs, c, bad, len(c), s)
+                out.append((c.tobytes(), p.tobytes(), bool(st.any() or st2.any()), ok, nok))
+            results[t] = out
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for t in range(4):
+        blobs, cms, proofs = sets[t]
+        for c, p, st, ok, nok in results[t]:
+            assert c == cms.tobytes() and p == proofs.tobytes() and not st and ok is True and nok is False

@@ -387,3 +387,19 @@ def test_trusted_setup_json_helper():
         k.TrustedSetup.from_json(json.dumps(bad))
     with pytest.raises(k.InvalidTrustedSetup):
         k.TrustedSetup.from_json("{}")
+
+
+def test_host_sha256_dispatch_vs_hashlib():
+    """compute_r_powers' sequential hash runs on the host (csrc/host_sha256.cpp): the SHA-NI path where the CPU has it
+    and the portable compression function, fed in odd-sized pieces, against hashlib."""
+    import hashlib
+    import kzg_rust_b200 as k
+    L = k.load_library()
+    L.kzg_b200_host_sha256.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_char_p]
+    rng = np.random.default_rng(8)
+    for n in [0, 1, 55, 56, 57, 63, 64, 65, 119, 120, 127, 128, 1000, 32 + 160 * 333]:
+        d = rng.bytes(n)
+        for portable in (0, 1):
+            out = ctypes.create_string_buffer(32)
+            L.kzg_b200_host_sha256(d, n, portable, out)
+            assert out.raw == hashlib.sha256(d).digest(), (n, portable)
