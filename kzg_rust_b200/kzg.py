@@ -66,10 +66,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise CudaError("libkzg_b200.so is missing; build it with `python -m kzg_rust_b200.build` "
-                        "(there is no CPU fallback)")
-    L = ctypes.CDLL(LIB_PATH)
+    path = os.environ.get("KZG_B200_LIB", LIB_PATH)  # experiments load a differently built copy (tools/variant_sweep.sh)
+    if not os.path.exists(path):
+        raise CudaError("%s is missing; build it with `python -m kzg_rust_b200.build` "
+                        "(there is no CPU fallback)" % os.path.basename(path))
+    L = ctypes.CDLL(path)
     vp, cp, sz, ci = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int
     pvp, pci = ctypes.POINTER(vp), ctypes.POINTER(ci)
     L.kzg_b200_ctx_create.argtypes = [vp, sz, vp, sz, ci, ci, pvp]

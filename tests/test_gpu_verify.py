@@ -11,6 +11,7 @@ from gpu_util import VECTOR_WIDTH_IDS, VECTOR_WIDTHS, gpu_settings, oracle_setti
 
 pytestmark = pytest.mark.gpu
 G = golden()
+R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
 
 
 def _kzg():
