@@ -61,10 +61,62 @@ __global__ void __launch_bounds__(64) k_horner_compress(const g1_affine_t *sums,
     for (int k = 0; k < 12; k++)
         o[k] = (uint32_t)buf[4 * k] | ((uint32_t)buf[4 * k + 1] << 8) | ((uint32_t)buf[4 * k + 2] << 16) | ((uint32_t)buf[4 * k + 3] << 24);
 }
+// The same with one WARP per blob, for small batches where the pass is pure latency (254 dependent doublings and
+// additions per blob, 4.5 ms): lane k folds the sums 8k .. 8k + 7, then five rounds join the 32 partial results,
+// T_k + 2^(8 s) T_(k + s) -- the doublings stay on the critical path (255 of them), the additions leave it (12
+// instead of 254).  2.0 ms per call.
+#define KZG_HORNER_WARP_MAX 1024
+__global__ void __launch_bounds__(128) k_horner_compress_warp(const g1_affine_t *sums, size_t stride, int W, const int32_t *status,
+                                                              uint8_t *out, uint32_t count) {
+    __shared__ g1_jac_t part[4][32];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * 4 + warp;
+    if (i >= count) return;  // the whole warp
+    uint32_t *o = reinterpret_cast<uint32_t *>(out + 48ull * i);
+    if (status && status[i] != KZG_OK) {
+        if (lane < 12) o[lane] = 0;
+        return;
+    }
+    const int lo = 8 * (int)lane, hi = min(lo + 8, W);
+    g1_jac_t acc;
+    g1j_set_inf(acc);
+#pragma unroll 1
+    for (int j = hi - 1; j >= lo; j--) {
+        g1j_dbl(acc, acc);
+        g1_affine_t sj = horner_load(sums + (size_t)j * stride + i);
+        if (!g1a_is_inf(sj)) g1j_add_affine(acc, acc, sj.x, sj.y);
+    }
+    part[warp][lane] = acc;
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t s = 1; s < 32; s <<= 1) {
+        if ((lane & (2 * s - 1)) == 0) {
+            g1_jac_t t = part[warp][lane + s];
+#pragma unroll 1
+            for (uint32_t d = 0; d < 8 * s; d++) g1j_dbl(t, t);
+            g1_jac_t a = part[warp][lane];
+            g1j_add(t, t, a);
+            part[warp][lane] = t;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        g1_affine_t p;
+        g1j_to_affine(p, part[warp][0]);
+        uint8_t buf[48];
+        g1a_compress(buf, p);
+#pragma unroll
+        for (int k = 0; k < 12; k++)
+            o[k] = (uint32_t)buf[4 * k] | ((uint32_t)buf[4 * k + 1] << 8) | ((uint32_t)buf[4 * k + 2] << 16) | ((uint32_t)buf[4 * k + 3] << 24);
+    }
+}
 int g1_launch_horner_compress(cudaStream_t st, const g1_affine_t *d_sums, size_t stride, int W, const int32_t *d_status,
                               uint8_t *d_out, size_t count) {
     if (count == 0) return KZG_B200_OK;
-    k_horner_compress<<<blocks_for(count, 64), 64, 0, st>>>(d_sums, stride, W, d_status, d_out, (uint32_t)count);
+    if (count <= KZG_HORNER_WARP_MAX && W <= 256)
+        k_horner_compress_warp<<<blocks_for(count, 4), 128, 0, st>>>(d_sums, stride, W, d_status, d_out, (uint32_t)count);
+    else
+        k_horner_compress<<<blocks_for(count, 64), 64, 0, st>>>(d_sums, stride, W, d_status, d_out, (uint32_t)count);
     CU(cudaGetLastError());
     return KZG_B200_OK;
 }

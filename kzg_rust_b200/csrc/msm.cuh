@@ -92,9 +92,7 @@ struct PairPolicy {
     const g1_affine_t *in;
     g1_affine_t *out;
     FastDiv R;
-    static constexpr bool prefetch_ahead = false;
     KZG_HD uint32_t digit(uint64_t, int) const { return 0; }
-    KZG_HD void prefetch(uint64_t, int, uint32_t) const {}
     KZG_HD const g1_affine_t *src_d(uint64_t g, int which, uint32_t, bool &neg) const { return src(g, which, neg); }
     KZG_HD const g1_affine_t *src(uint64_t g, int which, bool &neg) const {
         neg = false;
@@ -114,25 +112,9 @@ struct GatherPolicy {
     g1_affine_t *out;
     FastDiv R;
     uint32_t E;  // table entries per group, 2^(g-1)
-    // The digit is read ahead of the table entry it selects (digit -> address -> entry is a chain of two dependent
-    // loads), and in pass 1 -- one product per addition, too short to cover a random HBM access -- the entry is
-    // also pulled into L2 one iteration before it is loaded (ncu: 9.8 % of the gather level's stall samples were
-    // long-scoreboard waits on pass 1's first use of x).
-#ifndef KZG_GATHER_PREFETCH
-#define KZG_GATHER_PREFETCH 1
-#endif
-    static constexpr bool prefetch_ahead = KZG_GATHER_PREFETCH != 0;
-    KZG_HD void prefetch(uint64_t g, int which, uint32_t d) const {
-#if defined(__CUDA_ARCH__)
-        bool neg;
-        const g1_affine_t *p = src_d(g, which, d, neg);
-        // x is the first 48 bytes of the entry; entries are 32-byte aligned, so it may straddle two 64-byte lines
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p) + 32));
-#else
-        (void)g; (void)which; (void)d;
-#endif
-    }
+    // The digit is read one iteration before the table entry it selects (digit -> address -> entry is a
+    // chain of two dependent loads).  (Pulling the entry into L2 with prefetch.global.L2 one more iteration ahead
+    // was measured and made the level 25 % SLOWER -- profiles/sweep_r2c.log -- so it is not done.)
     KZG_HD uint32_t digit(uint64_t g, int which) const {
         uint32_t p = R.div((uint32_t)g);
         return digits[g + (uint64_t)(p + (uint32_t)which) * R.d];  // = (2p + which)*R + r
@@ -156,9 +138,7 @@ struct CombLevelPolicy {
     g1_affine_t *table;
     const g1_affine_t *bases;
     uint32_t g, m, upper;
-    static constexpr bool prefetch_ahead = false;
     KZG_HD uint32_t digit(uint64_t, int) const { return 0; }
-    KZG_HD void prefetch(uint64_t, int, uint32_t) const {}
     KZG_HD const g1_affine_t *src_d(uint64_t a, int which, uint32_t, bool &neg) const { return src(a, which, neg); }
     KZG_HD uint64_t slot(uint64_t a, uint32_t &q) const {
         q = (uint32_t)(a >> (m - 1));
@@ -307,14 +287,11 @@ KZG_HD void batch_add_thread(const Policy &pol, uint64_t total, fp_t *scratch, i
         int cnt = 0;
         fp_t nx1, nx2;
         uint32_t dn0 = 0, dn1 = 0;  // digits of the addition whose operands are requested next (gather level)
-        uint32_t dp0 = 0, dp1 = 0;  // ... and of the one after it, whose table entries are prefetched into L2
         {
             uint64_t g = base + tid;
             if (g < total) { load_x(pol, g, 0, nx1); load_x(pol, g, 1, nx2); }
             g += T;
             if (1 < k && g < total) { dn0 = pol.digit(g, 0); dn1 = pol.digit(g, 1); }
-            g += T;
-            if (Policy::prefetch_ahead && 2 < k && g < total) { dp0 = pol.digit(g, 0); dp1 = pol.digit(g, 1); }
         }
 #pragma unroll 1
         for (int j = 0; j < k; j++) {
@@ -324,16 +301,7 @@ KZG_HD void batch_add_thread(const Policy &pol, uint64_t total, fp_t *scratch, i
             uint64_t gn = g + T;
             if (j + 1 < k && gn < total) { load_x_d(pol, gn, 0, dn0, nx1); load_x_d(pol, gn, 1, dn1, nx2); }
             gn += T;
-            if (Policy::prefetch_ahead) {
-                if (j + 2 < k && gn < total) { pol.prefetch(gn, 0, dp0); pol.prefetch(gn, 1, dp1); }
-                dn0 = dp0;
-                dn1 = dp1;
-                gn += T;
-                if (j + 3 < k && gn < total) { dp0 = pol.digit(gn, 0); dp1 = pol.digit(gn, 1); }
-            } else if (j + 2 < k && gn < total) {
-                dn0 = pol.digit(gn, 0);
-                dn1 = pol.digit(gn, 1);
-            }
+            if (j + 2 < k && gn < total) { dn0 = pol.digit(gn, 0); dn1 = pol.digit(gn, 1); }
             add_denominator<Policy::lazy>(den, x1, x2, [&](fp_t &y) { load_y(pol, g, 0, y); }, [&](fp_t &y) { load_y(pol, g, 1, y); });
             st_fp(scratch + (uint64_t)j * T + tid, acc);
             fpx_mul<Policy::lazy>(acc, acc, den);

@@ -49,6 +49,7 @@ def lib():
         L.ko_verify_blob_kzg_proof_batch.argtypes = [vp, cp, cp, cp, sz, pi]
         L.ko_blob_to_kzg_commitment_many.argtypes = [vp, vp, sz, vp, vp, ci]
         L.ko_compute_blob_kzg_proof_many.argtypes = [vp, vp, vp, sz, vp, vp, ci]
+        L.ko_blob_to_kzg_commitment_many_fast.argtypes = [vp, vp, sz, vp, vp, ci]
         L.ko_compute_challenge.argtypes = [vp, cp, cp, cp]
         L.ko_evaluate_polynomial.argtypes = [vp, cp, cp, cp]
         L.ko_validate_kzg_g1.argtypes = [cp]
@@ -136,6 +137,18 @@ class OracleSettings:
         status = np.zeros(n, dtype=np.int32)
         lib().ko_blob_to_kzg_commitment_many(self._h, blobs_np.ctypes.data, n, out.ctypes.data,
                                              status.ctypes.data, nthreads)
+        return out, status
+
+    def blob_to_kzg_commitment_many_fast(self, blobs_np, nthreads=1):
+        """The timed CPU baseline (bench.py): the same bytes as blob_to_kzg_commitment_many from the fast
+        restatement of the bucket method (batch-affine buckets, mulx Montgomery) -- see kzg_oracle.c."""
+        import numpy as np
+        blobs_np = np.ascontiguousarray(blobs_np)
+        n = blobs_np.size // self.bytes_per_blob
+        out = np.zeros((n, 48), dtype=np.uint8)
+        status = np.zeros(n, dtype=np.int32)
+        lib().ko_blob_to_kzg_commitment_many_fast(self._h, blobs_np.ctypes.data, n, out.ctypes.data,
+                                                  status.ctypes.data, nthreads)
         return out, status
 
     def compute_blob_kzg_proof_many(self, blobs_np, commitments_np, nthreads=1):

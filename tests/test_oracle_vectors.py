@@ -3,6 +3,7 @@ reference ships (reference tests/*/small/*/data.yaml -> tests/golden/, 208 cases
 under the reference runner's contract (reference src/lib.rs:14-204): an input that
 fails to parse, or an API `Err`, must coincide with `output: null`; otherwise the
 outputs must be byte-equal."""
+import os
 import pytest
 
 from golden_util import golden
@@ -129,3 +130,33 @@ def test_verify_blob_kzg_proof_batch(s, case):
         assert case["output"] is None
         return
     assert ok is case["output"]
+
+
+def test_fast_cpu_baseline_path_matches_the_checker():
+    """bench.py times `blob_to_kzg_commitment_many_fast` (batch-affine buckets, mulx Montgomery) as the CPU baseline:
+    it must give the checker's bytes -- on the reference's commitment vectors (status included), on the
+    adversarially regular blobs and on random ones."""
+    import numpy as np
+    from gpu_util import oracle_settings, synthetic_blobs
+    o = oracle_settings("mainnet")
+    G = golden()
+    R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    cases = [c for c in G.by_fn("blob_to_kzg_commitment") if len(G.get_bytes(c["input"]["blob"])) == 131072]
+    vec = np.frombuffer(b"".join(G.get_bytes(c["input"]["blob"]) for c in cases), dtype=np.uint8).reshape(len(cases), 131072)
+    extra = synthetic_blobs(6, seed=21)
+    extra[0, :] = 0
+    extra[1, :] = 0
+    extra[1, 31::32] = 1
+    extra[2] = np.frombuffer((R - 1).to_bytes(32, "big") * 4096, dtype=np.uint8)
+    extra[3, 32 * 7:32 * 8] = 0xff
+    blobs = np.concatenate([vec, extra], axis=0)
+    exp, est = o.blob_to_kzg_commitment_many(blobs, nthreads=os.cpu_count() or 1)
+    got, gst = o.blob_to_kzg_commitment_many_fast(blobs, nthreads=os.cpu_count() or 1)
+    assert np.array_equal(est, gst)
+    ok = est == 0
+    assert ok.sum() >= 8 and np.array_equal(exp[ok], got[ok])
+    for i, c in enumerate(cases):
+        if c["output"] is None:
+            assert gst[i] != 0
+        else:
+            assert "0x" + got[i].tobytes().hex() == c["output"]
