@@ -1,0 +1,17 @@
+#!/bin/bash
+# compute-sanitizer over the reference's vectors on the small comb (g = 8): memcheck on commitments, blob proofs and
+# batch verification, racecheck (shared-memory hazards: the block-wide inversion, the evaluation kernel's scans, the
+# warp-cooperative Horner pass) on commitments and blob proofs.  Usage (on the GPU box): bash tools/sanitize.sh <tag>
+TAG=${1:-r2}
+mkdir -p gpurun_out
+OUT=gpurun_out/sanitizer_$TAG.txt
+: > $OUT
+run() {
+  echo "== compute-sanitizer --tool $1 :: $2 -k '$3'" | tee -a $OUT
+  timeout 1500 compute-sanitizer --tool $1 --error-exitcode 9 --print-limit 5 python -m pytest -x -q "$2" -k "$3" 2>&1 | grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY|Invalid|hazard|error" | tail -8 | tee -a $OUT
+}
+run memcheck tests/test_gpu_commit.py "g8"
+run memcheck tests/test_gpu_proof.py "compute_blob_kzg_proof_vectors and g8"
+run memcheck tests/test_gpu_verify.py "verify_blob_kzg_proof_batch_vectors and g8"
+run racecheck tests/test_gpu_commit.py "reference_vectors and g8"
+run racecheck tests/test_gpu_proof.py "compute_blob_kzg_proof_vectors and g8"
