@@ -54,7 +54,7 @@ KZG_HD void st_fp(fp_t *p, const fp_t &r) {
 }
 
 // ------------------------------------------------------------------ where the operands of addition #g live
-// A policy maps the flat addition index g to two source points (nullptr = infinity, with
+// A policy maps the flat addition index g to two source points (a stored point; infinity carries its marker, with
 // an optional negation of y) and one destination.
 
 // Division of a 32-bit index by a launch constant (the rows-per-point count R below) without a
@@ -157,53 +157,30 @@ struct CombLevelPolicy {
     }
 };
 
+// Operand loads.  No policy has a "missing operand": a point at infinity is a stored point with the marker in x
+// (g1.cuh), so the loads are unconditional and the special cases are found by looking at the values.
 template <class Policy>
 KZG_HD void load_x(const Policy &pol, uint64_t g, int which, fp_t &x) {
     bool neg;
-    const g1_affine_t *p = pol.src(g, which, neg);
-    if (p == nullptr) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) x.l[i] = 0xffffffffu;
-    } else {
-        ld_fp(x, &p->x);
-    }
+    ld_fp(x, &pol.src(g, which, neg)->x);
 }
 template <class Policy>
 KZG_HD void load_y(const Policy &pol, uint64_t g, int which, fp_t &y) {
     bool neg;
     const g1_affine_t *p = pol.src(g, which, neg);
-    if (p == nullptr) { fe_set_zero(y); return; }
     ld_fp(y, &p->y);
     if (neg) fe_neg(y, y);
 }
-
 template <class Policy>
 KZG_HD void load_x_d(const Policy &pol, uint64_t g, int which, uint32_t d, fp_t &x) {
     bool neg;
-    const g1_affine_t *p = pol.src_d(g, which, d, neg);
-    if (p == nullptr) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) x.l[i] = 0xffffffffu;
-    } else {
-        ld_fp(x, &p->x);
-    }
+    ld_fp(x, &pol.src_d(g, which, d, neg)->x);
 }
-template <class Policy>
-KZG_HD void load_y_d(const Policy &pol, uint64_t g, int which, uint32_t d, fp_t &y) {
-    bool neg;
-    const g1_affine_t *p = pol.src_d(g, which, d, neg);
-    if (p == nullptr) { fe_set_zero(y); return; }
-    ld_fp(y, &p->y);
-    if (neg) fe_neg(y, y);
-}
-
 // y as stored, with the sign still to be applied: the negation is the first consumer of the load, so it is
 // deferred until two products later (ncu: 11 % of the gather level's stall samples sat on it)
 template <class Policy>
 KZG_HD void load_y_raw_d(const Policy &pol, uint64_t g, int which, uint32_t d, fp_t &y, bool &neg) {
-    const g1_affine_t *p = pol.src_d(g, which, d, neg);
-    if (p == nullptr) { fe_set_zero(y); neg = false; return; }
-    ld_fp(y, &p->y);
+    ld_fp(y, &pol.src_d(g, which, d, neg)->y);
 }
 
 // ------------------------------------------------------------------ the hot kernel
@@ -275,6 +252,11 @@ KZG_HD void shared_inverse(fp_t &inv, const fp_t &acc) { fp_inv(inv, acc); }
 #ifndef KZG_ADD_MIN_BLOCKS
 #define KZG_ADD_MIN_BLOCKS 3
 #endif
+#ifndef KZG_ADD_UNROLL
+#define KZG_ADD_UNROLL 1
+#endif
+#define KZG_PRAGMA_(x) _Pragma(#x)
+#define KZG_UNROLL(n) KZG_PRAGMA_(unroll n)
 // One thread's share; a plain function so a CPU test can walk it thread by thread.
 // Both passes are software-pipelined: the operands of the next addition are requested before
 // the multiplications of the current one, so the (random, for the gather level) HBM
@@ -293,7 +275,7 @@ KZG_HD void batch_add_thread(const Policy &pol, uint64_t total, fp_t *scratch, i
             g += T;
             if (1 < k && g < total) { dn0 = pol.digit(g, 0); dn1 = pol.digit(g, 1); }
         }
-#pragma unroll 1
+KZG_UNROLL(KZG_ADD_UNROLL)
         for (int j = 0; j < k; j++) {
             uint64_t g = base + (uint64_t)j * T + tid;
             if (g >= total) break;
@@ -323,7 +305,7 @@ KZG_HD void batch_add_thread(const Policy &pol, uint64_t total, fp_t *scratch, i
             ld_fp(npre, scratch + (uint64_t)(cnt - 1) * T + tid);
             if (cnt > 1) { dn0 = pol.digit(g - T, 0); dn1 = pol.digit(g - T, 1); }
         }
-#pragma unroll 1
+KZG_UNROLL(KZG_ADD_UNROLL)
         for (int j = cnt - 1; j >= 0; j--) {
             uint64_t g = base + (uint64_t)j * T + tid;
             g1_affine_t p1, p2, r;

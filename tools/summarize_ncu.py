@@ -4,6 +4,10 @@
     ncu -i X.ncu-rep --page raw --csv    > raw.csv
     ncu -i X.ncu-rep --page source --csv > source.csv
     python tools/summarize_ncu.py raw.csv source.csv > profiles/<name>.md
+    python tools/summarize_ncu.py raw.csv --traffic profiles/ncu_traffic.json 23 profiles/<name>.md
+
+The second form records the DRAM bytes of the captured gather-level and pair-level launches (one 4096-blob chunk) as
+bytes per average batch_add launch for comb width 23; bench.py reports that number as roofline.traffic.
 """
 import collections
 import csv
@@ -18,7 +22,39 @@ RAW_KEYS = [
 ]
 
 
+def traffic(raw, out, comb_width, source):
+    """gather-level launch + the tree levels (the captured first pair level scaled by the additions of all of them)"""
+    import json
+    import os
+    rows = list(csv.reader(open(raw)))
+    hdr, data = rows[0], rows[2:]
+    name_i, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    u_rd, u_wr = unit[rows[1][rd]], unit[rows[1][wr]]
+    by = {}
+    for r in data:
+        key = "gather" if "GatherPolicy" in r[name_i] else "pair" if "PairPolicy" in r[name_i] else None
+        if key and key not in by:
+            by[key] = float(r[rd]) * u_rd + float(r[wr]) * u_wr
+    groups = -(-4096 // comb_width)
+    level_rows, pair_adds = (groups + 1) // 2, []
+    while level_rows > 1:
+        pair_adds.append(level_rows // 2)
+        level_rows = (level_rows + 1) // 2
+    tree = by["pair"] * sum(pair_adds) / pair_adds[0]
+    launches = 1 + len(pair_adds)
+    doc = json.load(open(out)) if os.path.exists(out) else {}
+    doc[str(comb_width)] = {"dram_bytes_per_avg_launch": (by["gather"] + tree) / launches, "launches_per_chunk": launches,
+                            "gather_launch_bytes": by["gather"], "first_pair_launch_bytes": by["pair"],
+                            "dram_bytes_per_blob": (by["gather"] + tree) / 4096, "source": source}
+    json.dump(doc, open(out, "w"), indent=1, sort_keys=True)
+    print(json.dumps(doc[str(comb_width)]))
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[2] == "--traffic":
+        traffic(sys.argv[1], sys.argv[3], int(sys.argv[4]), sys.argv[5])
+        return
     raw, src = sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None
     rows = list(csv.reader(open(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
