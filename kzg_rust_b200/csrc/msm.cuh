@@ -114,7 +114,9 @@ struct GatherPolicy {
     uint32_t E;  // table entries per group, 2^(g-1)
     // The digit is read one iteration before the table entry it selects (digit -> address -> entry is a
     // chain of two dependent loads).  (Pulling the entry into L2 with prefetch.global.L2 one more iteration ahead
-    // was measured and made the level 25 % SLOWER -- profiles/sweep_r2c.log -- so it is not done.)
+    // was measured and made the level 25 % SLOWER -- profiles/sweep_r2c.log -- and requesting the operands two
+    // additions ahead in registers made it 8 % slower -- profiles/sweep_r2f.log: the level is limited by the rate
+    // of random 64-byte DRAM accesses, not by their latency, so neither is done.)
     KZG_HD uint32_t digit(uint64_t g, int which) const {
         uint32_t p = R.div((uint32_t)g);
         return digits[g + (uint64_t)(p + (uint32_t)which) * R.d];  // = (2p + which)*R + r
