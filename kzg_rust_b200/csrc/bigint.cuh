@@ -221,6 +221,87 @@ template <class P, bool REDUCE> KZG_HD void fe_mul_core(Fe<P> &r, const Fe<P> &a
 template <class P> KZG_HD void fe_mul(Fe<P> &r, const Fe<P> &a, const Fe<P> &b) { fe_mul_core<P, true>(r, a, b); }
 template <class P> KZG_HD void fe_sqr(Fe<P> &r, const Fe<P> &a) { fe_mul(r, a, a); }
 
+// Two independent products at once: r1 = a1 b1, r2 = a2 b2, the carry chains of the two interleaved chain by chain.
+// One product is a dependent sequence of ~290 multiply-adds, and a lone warp issues it at half the rate of the
+// multiplier (the next instruction of a chain waits for the previous one); a second, independent chain in the gaps
+// nearly doubles what a latency-bound thread gets done -- the Jacobian formulas of the Horner pass, the scalar
+// ladders and the subgroup checks pair their products through this (g1.cuh).  Same steps as fe_mul_core.
+template <class P> KZG_HD void mul2_step_a(uint32_t *E, uint32_t *O, const uint32_t *a, uint32_t bi) {
+    constexpr int N = P::N;
+    uint32_t cc = 0;
+    E[0] = add_cc(E[0], O[1], cc);
+#pragma unroll
+    for (int k = 0; k < N - 2; k += 2) {
+        O[k] = madc_lo_cc(a[k + 1], bi, O[k + 2], cc);
+        O[k + 1] = madc_hi_cc(a[k + 1], bi, O[k + 3], cc);
+    }
+    O[N - 2] = madc_lo_cc(a[N - 1], bi, 0, cc);
+    O[N - 1] = madc_hi(a[N - 1], bi, 0, cc);
+}
+template <class P> KZG_HD void mul2_step_b(uint32_t *E, uint32_t *O, const uint32_t *a, uint32_t bi) {
+    uint32_t cc = 0;
+    cmad_row<P::N>(E, a, bi, cc);
+    O[P::N - 1] = addc(O[P::N - 1], 0, cc);
+}
+template <class P> KZG_HD uint32_t mul2_step_c(uint32_t *E, uint32_t *O, const uint32_t *mp) {
+    uint32_t cc = 0;
+    uint32_t m = mul_lo(E[0], P::n0);
+    cmad_row<P::N>(O, mp + 1, m, cc);
+    return m;
+}
+template <class P> KZG_HD void mul2_step_d(uint32_t *E, uint32_t *O, const uint32_t *mp, uint32_t m) {
+    uint32_t cc = 0;
+    cmad_row<P::N>(E, mp, m, cc);
+    O[P::N - 1] = addc(O[P::N - 1], 0, cc);
+}
+template <class P> KZG_HD void mul2_finish(Fe<P> &r, const uint32_t *E, const uint32_t *O) {
+    constexpr int N = P::N;
+    uint32_t cc = 0;
+    Fe<P> t;
+    t.l[0] = add_cc(O[0], E[1], cc);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) t.l[k] = addc_cc(O[k], E[k + 1], cc);
+    t.l[N - 1] = addc(O[N - 1], 0, cc);
+    fe_reduce_once(t, 0);
+    r = t;
+}
+template <class P> KZG_HD void fe_mul2(Fe<P> &r1, const Fe<P> &a1, const Fe<P> &b1, Fe<P> &r2, const Fe<P> &a2, const Fe<P> &b2) {
+    constexpr int N = P::N;
+    uint32_t mp[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) mp[i] = P::mod(i);
+    uint32_t x1[N], y1[N], x2[N], y2[N];
+    // step 0
+    mul_row<N>(x1, a1.l, b1.l[0]);
+    mul_row<N>(x2, a2.l, b2.l[0]);
+    mul_row<N>(y1, a1.l + 1, b1.l[0]);
+    mul_row<N>(y2, a2.l + 1, b2.l[0]);
+    {
+        uint32_t m1 = mul2_step_c<P>(x1, y1, mp);
+        uint32_t m2 = mul2_step_c<P>(x2, y2, mp);
+        mul2_step_d<P>(x1, y1, mp, m1);
+        mul2_step_d<P>(x2, y2, mp, m2);
+    }
+#pragma unroll
+    for (int i = 1; i < N; i++) {
+        uint32_t *E1 = (i & 1) ? y1 : x1, *O1 = (i & 1) ? x1 : y1;
+        uint32_t *E2 = (i & 1) ? y2 : x2, *O2 = (i & 1) ? x2 : y2;
+        mul2_step_a<P>(E1, O1, a1.l, b1.l[i]);
+        mul2_step_a<P>(E2, O2, a2.l, b2.l[i]);
+        mul2_step_b<P>(E1, O1, a1.l, b1.l[i]);
+        mul2_step_b<P>(E2, O2, a2.l, b2.l[i]);
+        uint32_t m1 = mul2_step_c<P>(E1, O1, mp);
+        uint32_t m2 = mul2_step_c<P>(E2, O2, mp);
+        mul2_step_d<P>(E1, O1, mp, m1);
+        mul2_step_d<P>(E2, O2, mp, m2);
+    }
+    Fe<P> t1, t2;  // the outputs may alias the inputs
+    mul2_finish<P>(t1, ((N - 1) & 1) ? y1 : x1, ((N - 1) & 1) ? x1 : y1);
+    mul2_finish<P>(t2, ((N - 1) & 1) ? y2 : x2, ((N - 1) & 1) ? x2 : y2);
+    r1 = t1;
+    r2 = t2;
+}
+
 // ------------------------------------------------------------------ lazy residues: values in [0, 2 mod)
 // Every instruction beside the multiplier costs issue slots, so the hot loop of
 // the MSM keeps its values only partly reduced.  With R = 2^(32N) > 4 mod (Fp: R / mod = 9.8) the

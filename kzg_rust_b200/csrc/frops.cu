@@ -11,7 +11,10 @@ int fr_setup_roots_device(int n, fr_t **d_roots, cudaStream_t stream) { return f
 
 int fr_launch_challenge(cudaStream_t st, const uint8_t *d_blobs, const uint8_t *d_commitments, size_t count, int n, fr_t *d_z) {
     if (count == 0) return KZG_B200_OK;
-    k_challenge<<<blocks_for(count, 64), 64, 0, st>>>(d_blobs, d_commitments, (uint32_t)count, n, d_z);
+    if (count <= KZG_CHALLENGE_WARP_MAX)
+        k_challenge_warp<<<blocks_for(count, 4), 128, 0, st>>>(d_blobs, d_commitments, (uint32_t)count, n, d_z);
+    else
+        k_challenge<<<blocks_for(count, 64), 64, 0, st>>>(d_blobs, d_commitments, (uint32_t)count, n, d_z);
     CU(cudaGetLastError());
     return KZG_B200_OK;
 }

@@ -94,17 +94,19 @@ KZG_HD void g1j_from_affine(g1_jac_t &r, const g1_affine_t &a) {
     if (g1a_is_inf(a)) { g1j_set_inf(r); return; }
     r.x = a.x; r.y = a.y; r.z = fe_one<FpParams>();
 }
+// The Jacobian formulas below run where one thread owns a long dependent chain (the Horner pass, the scalar
+// ladders, the subgroup checks, the sums of batch verification): their products are issued in independent PAIRS
+// (fe_mul2, bigint.cuh) so that a latency-bound thread keeps two carry chains in flight.
 KZG_HD void g1j_dbl(g1_jac_t &r, const g1_jac_t &p) {
     // a = 0 doubling; infinity maps to infinity because Z3 = 2 Y Z
-    fp_t A, B, C, D, E, F, t;
-    fe_sqr(A, p.x);
-    fe_sqr(B, p.y);
-    fe_sqr(C, B);
-    fe_add(t, p.x, B); fe_sqr(t, t); fe_sub(t, t, A); fe_sub(t, t, C); fe_dbl(D, t);
+    fp_t A, B, C, D, E, F, t, z3;
+    fe_mul2(A, p.x, p.x, B, p.y, p.y);
+    fe_add(t, p.x, B);
+    fe_mul2(C, B, B, t, t, t);
+    fe_sub(t, t, A); fe_sub(t, t, C); fe_dbl(D, t);
     fe_dbl(E, A); fe_add(E, E, A);
-    fe_sqr(F, E);
-    fp_t z3;
-    fe_mul(z3, p.y, p.z); fe_dbl(z3, z3);
+    fe_mul2(F, E, E, z3, p.y, p.z);
+    fe_dbl(z3, z3);
     fe_dbl(t, D); fe_sub(r.x, F, t);
     fe_sub(t, D, r.x); fe_mul(t, E, t);
     fe_dbl(C, C); fe_dbl(C, C); fe_dbl(C, C);
@@ -114,57 +116,57 @@ KZG_HD void g1j_dbl(g1_jac_t &r, const g1_jac_t &p) {
 // r = p + q (q affine, not infinity), complete
 KZG_HD void g1j_add_affine(g1_jac_t &r, const g1_jac_t &p, const fp_t &qx, const fp_t &qy) {
     if (g1j_is_inf(p)) { r.x = qx; r.y = qy; r.z = fe_one<FpParams>(); return; }
-    fp_t z1z1, u2, s2, h, hh, i, j, rr, v, t;
-    fe_sqr(z1z1, p.z);
-    fe_mul(u2, qx, z1z1);
-    fe_mul(s2, qy, p.z); fe_mul(s2, s2, z1z1);
+    fp_t z1z1, u2, s2, h, hh, i, j, rr, v, t, tz;
+    fe_mul2(z1z1, p.z, p.z, s2, qy, p.z);
+    fe_mul2(u2, qx, z1z1, s2, s2, z1z1);
     if (fe_eq(p.x, u2)) {
         if (fe_eq(p.y, s2)) { g1j_dbl(r, p); return; }
         g1j_set_inf(r);
         return;
     }
     fe_sub(h, u2, p.x);
-    fe_sqr(hh, h);
+    fe_add(tz, p.z, h);
+    fe_mul2(hh, h, h, tz, tz, tz);
     fe_dbl(i, hh); fe_dbl(i, i);
-    fe_mul(j, h, i);
+    fe_mul2(j, h, i, v, p.x, i);
     fe_sub(rr, s2, p.y); fe_dbl(rr, rr);
-    fe_mul(v, p.x, i);
     fp_t x3, y3, z3;
-    fe_sqr(x3, rr); fe_sub(x3, x3, j); fe_dbl(t, v); fe_sub(x3, x3, t);
+    fe_mul2(x3, rr, rr, s2, p.y, j);
+    fe_sub(x3, x3, j); fe_dbl(t, v); fe_sub(x3, x3, t);
     fe_sub(t, v, x3); fe_mul(t, rr, t);
-    fe_mul(s2, p.y, j); fe_dbl(s2, s2);
+    fe_dbl(s2, s2);
     fe_sub(y3, t, s2);
-    fe_add(t, p.z, h); fe_sqr(t, t); fe_sub(t, t, z1z1); fe_sub(z3, t, hh);
+    fe_sub(tz, tz, z1z1); fe_sub(z3, tz, hh);
     r.x = x3; r.y = y3; r.z = z3;
 }
 // r = p + q, both Jacobian, complete
 KZG_HD void g1j_add(g1_jac_t &r, const g1_jac_t &p, const g1_jac_t &q) {
     if (g1j_is_inf(p)) { r = q; return; }
     if (g1j_is_inf(q)) { r = p; return; }
-    fp_t z1z1, z2z2, u1, u2, s1, s2, h, i, j, rr, v, t;
-    fe_sqr(z1z1, p.z);
-    fe_sqr(z2z2, q.z);
-    fe_mul(u1, p.x, z2z2);
-    fe_mul(u2, q.x, z1z1);
-    fe_mul(s1, p.y, q.z); fe_mul(s1, s1, z2z2);
-    fe_mul(s2, q.y, p.z); fe_mul(s2, s2, z1z1);
+    fp_t z1z1, z2z2, u1, u2, s1, s2, h, i, j, rr, v, t, tz;
+    fe_mul2(z1z1, p.z, p.z, z2z2, q.z, q.z);
+    fe_mul2(u1, p.x, z2z2, u2, q.x, z1z1);
+    fe_mul2(s1, p.y, q.z, s2, q.y, p.z);
+    fe_mul2(s1, s1, z2z2, s2, s2, z1z1);
     if (fe_eq(u1, u2)) {
         if (fe_eq(s1, s2)) { g1j_dbl(r, p); return; }
         g1j_set_inf(r);
         return;
     }
     fe_sub(h, u2, u1);
-    fe_dbl(i, h); fe_sqr(i, i);
-    fe_mul(j, h, i);
+    fe_dbl(i, h);
+    fe_add(tz, p.z, q.z);
+    fe_mul2(i, i, i, tz, tz, tz);
+    fe_mul2(j, h, i, v, u1, i);
     fe_sub(rr, s2, s1); fe_dbl(rr, rr);
-    fe_mul(v, u1, i);
     fp_t x3, y3, z3;
-    fe_sqr(x3, rr); fe_sub(x3, x3, j); fe_dbl(t, v); fe_sub(x3, x3, t);
-    fe_sub(t, v, x3); fe_mul(t, rr, t);
-    fe_mul(s1, s1, j); fe_dbl(s1, s1);
+    fe_mul2(x3, rr, rr, s1, s1, j);
+    fe_sub(x3, x3, j); fe_dbl(t, v); fe_sub(x3, x3, t);
+    fe_sub(t, v, x3);
+    fe_sub(tz, tz, z1z1); fe_sub(tz, tz, z2z2);
+    fe_mul2(t, rr, t, z3, tz, h);
+    fe_dbl(s1, s1);
     fe_sub(y3, t, s1);
-    fe_add(t, p.z, q.z); fe_sqr(t, t); fe_sub(t, t, z1z1); fe_sub(t, t, z2z2);
-    fe_mul(z3, t, h);
     r.x = x3; r.y = y3; r.z = z3;
 }
 KZG_HD void g1j_to_affine(g1_affine_t &r, const g1_jac_t &p) {

@@ -4,6 +4,11 @@
 #include "../../tools/experiments/fp_hybrid.cuh"
 using namespace kzg;
 extern "C" {
+void shim_fp_mul2(const uint32_t *a1, const uint32_t *b1, const uint32_t *a2, const uint32_t *b2, uint32_t *r1, uint32_t *r2) {
+    fp_t x1, y1, x2, y2; memcpy(x1.l, a1, 48); memcpy(y1.l, b1, 48); memcpy(x2.l, a2, 48); memcpy(y2.l, b2, 48);
+    fe_mul2(x1, x1, y1, y2, x2, y2);  /* outputs alias inputs on purpose */
+    memcpy(r1, x1.l, 48); memcpy(r2, y2.l, 48);
+}
 void shim_fp_mul(const uint32_t *a, const uint32_t *b, uint32_t *r) { fp_t x, y, z; memcpy(x.l, a, 48); memcpy(y.l, b, 48); fe_mul(z, x, y); memcpy(r, z.l, 48); }
 void shim_fp_add(const uint32_t *a, const uint32_t *b, uint32_t *r) { fp_t x, y, z; memcpy(x.l, a, 48); memcpy(y.l, b, 48); fe_add(z, x, y); memcpy(r, z.l, 48); }
 void shim_fp_sub(const uint32_t *a, const uint32_t *b, uint32_t *r) { fp_t x, y, z; memcpy(x.l, a, 48); memcpy(y.l, b, 48); fe_sub(z, x, y); memcpy(r, z.l, 48); }

@@ -403,3 +403,16 @@ def test_host_sha256_dispatch_vs_hashlib():
             out = ctypes.create_string_buffer(32)
             L.kzg_b200_host_sha256(d, n, portable, out)
             assert out.raw == hashlib.sha256(d).digest(), (n, portable)
+
+
+def test_paired_multiplication_vs_python(field):
+    """fe_mul2 (bigint.cuh): two independent Montgomery products with interleaved carry chains, outputs aliasing inputs."""
+    rng = np.random.default_rng(12)
+    Rp_inv = pow(pow(2, 384, P), -1, P)
+    edge = [0, 1, P - 1, P - 2, (P - 1) // 2, 2 ** 380]
+    vals = edge + [int.from_bytes(rng.bytes(48), "big") % P for _ in range(120)]
+    r1, r2 = (ctypes.c_uint32 * 12)(), (ctypes.c_uint32 * 12)()
+    for i in range(0, len(vals) - 3):
+        a1, b1, a2, b2 = vals[i], vals[i + 1], vals[i + 2], vals[i + 3]
+        field.shim_fp_mul2(_limbs(a1, 12), _limbs(b1, 12), _limbs(a2, 12), _limbs(b2, 12), r1, r2)
+        assert _val(r1) == a1 * b1 * Rp_inv % P and _val(r2) == a2 * b2 * Rp_inv % P

@@ -24,7 +24,7 @@ from gpu_util import synthetic_blobs  # noqa: E402
 samples = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 100
 with_cpu = "--cpu" in sys.argv
 g = golden()
-s = k.KzgSettings.load_trusted_setup(g.g1_bytes, g.g2_bytes, 0, int(os.environ.get("KZG_CRITERION_WINDOW_BITS", 0)))
+s = k.KzgSettings.load_trusted_setup(g.g1_bytes, g.g2_bytes, 0, int(os.environ.get("KZG_CRITERION_COMB_WIDTH", 0)))
 max_count = 64                                    # benches/kzg_benches.rs:26
 blobs = synthetic_blobs(max_count, seed=0xC817)   # :14-23, seeded
 cms, st = k.Kzg.blob_to_kzg_commitment_batch(blobs, s)
