@@ -52,7 +52,7 @@ def test_yaml_runner_on_the_oracle(tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
     assert "total %d, mismatches 0" % len(cases) in out.stdout
     # a wrong expected output is reported
-    bad = dict(cases[2], name="tampered", output="0x" + "c0" + "00" * 47) if cases[2]["fn"] == "blob_to_kzg_commitment" else None
+    bad = dict(cases[2], name="tampered", output="0x" + "a1" * 48) if cases[2]["fn"] == "blob_to_kzg_commitment" else None
     if bad:
         _write_tree(tree, [bad])
         out = _run(tree, setup, "--oracle")
