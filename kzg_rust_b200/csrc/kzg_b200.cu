@@ -310,12 +310,14 @@ extern "C" int kzg_b200_profile_read(kzg_b200_ctx *ctx, double *ms_out, uint64_t
 struct DeferredCompress {
     g1_affine_t *sums = nullptr;  // nullptr: compress per chunk
     size_t n = 0;                 // blobs of the whole call = row pitch of `sums`
+    uint8_t *out = nullptr;       // n x 48 B and n x int32 of the whole call, for host-buffer calls (they come after `sums`)
+    int32_t *status = nullptr;
 };
 static int deferred_begin(kzg_b200_ctx *ctx, size_t n, DeferredCompress *dc) {
     dc->sums = nullptr;
     dc->n = n;
     if (n <= ctx->chunk) return KZG_B200_OK;
-    const size_t elems = n * (size_t)ctx->W;
+    const size_t elems = n * (size_t)ctx->W + n;  // + n x 96 B: room for the call's outputs (48 B) and status words
     if (elems > ctx->sums_all_elems) {
         if (ctx->d_sums_all) CU(cudaFree(ctx->d_sums_all));
         ctx->d_sums_all = nullptr;
@@ -324,6 +326,8 @@ static int deferred_begin(kzg_b200_ctx *ctx, size_t n, DeferredCompress *dc) {
         ctx->sums_all_elems = elems;
     }
     dc->sums = ctx->d_sums_all;
+    dc->out = reinterpret_cast<uint8_t *>(ctx->d_sums_all + n * (size_t)ctx->W);
+    dc->status = reinterpret_cast<int32_t *>(dc->out + 48 * n);
     return KZG_B200_OK;
 }
 // after msm_run of one chunk (its sums are [bit position][count] in the lane's buffer): compress now, or park them
@@ -389,8 +393,9 @@ extern "C" int kzg_b200_blob_to_kzg_commitment_device(kzg_b200_ctx *ctx, const u
 // (on copy_stream) overlap the kernels of the current ones (one chunk per lane in flight).
 // upload(slot, off, cnt) enqueues the H2D copies of one chunk on copy_stream; run(slot, off, cnt)
 // enqueues kernels + D2H on the current lane's stream.
-template <class Upload, class Run>
-static int staged_chunks(kzg_b200_ctx *ctx, size_t n, Upload upload, Run run) {
+// finish() runs once after the lanes have joined, on the caller-visible stream, before the call waits for it.
+template <class Upload, class Run, class Finish>
+static int staged_chunks(kzg_b200_ctx *ctx, size_t n, Upload upload, Run run, Finish finish) {
     const size_t nchunks = (n + ctx->chunk - 1) / ctx->chunk;
     const size_t ahead = KZG_SLOTS - 1;
     auto enqueue_upload = [&](size_t i) -> int {
@@ -415,9 +420,14 @@ static int staged_chunks(kzg_b200_ctx *ctx, size_t n, Upload upload, Run run) {
         CU(cudaEventRecord(ctx->ev_free[slot], ctx->cur->stream));
     }
     RC(lanes_end(ctx));
+    RC(finish());
     CU(cudaStreamSynchronize(ctx->stream));
     stage_collect(ctx);
     return KZG_B200_OK;
+}
+template <class Upload, class Run>
+static int staged_chunks(kzg_b200_ctx *ctx, size_t n, Upload upload, Run run) {
+    return staged_chunks(ctx, n, upload, run, []() -> int { return KZG_B200_OK; });
 }
 
 extern "C" int kzg_b200_blob_to_kzg_commitment_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, size_t n, uint8_t *out,
@@ -426,6 +436,9 @@ extern "C" int kzg_b200_blob_to_kzg_commitment_batch(kzg_b200_ctx *ctx, const ui
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     const size_t bpb = (size_t)ctx->n * 32, ch = ctx->chunk;
+    // calls over several chunks run the Horner + compression pass once at the end, like the device-resident form
+    DeferredCompress dc;
+    RC(deferred_begin(ctx, n, &dc));
     return staged_chunks(
         ctx, n,
         [&](int slot, size_t off, size_t cnt) -> int {
@@ -433,11 +446,20 @@ extern "C" int kzg_b200_blob_to_kzg_commitment_batch(kzg_b200_ctx *ctx, const ui
             return KZG_B200_OK;
         },
         [&](int slot, size_t off, size_t cnt) -> int {
-            uint8_t *d_out = ctx->d_stage_out + slot * ch * 96;
-            int32_t *d_st = ctx->d_status + slot * ch;
-            RC(commit_chunk(ctx, ctx->d_stage_in + slot * ch * bpb, cnt, d_out, d_st));
-            CU(cudaMemcpyAsync(out + off * 48, d_out, cnt * 48, cudaMemcpyDeviceToHost, ctx->cur->stream));
-            CU(cudaMemcpyAsync(status + off, d_st, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->cur->stream));
+            uint8_t *d_out = dc.sums ? dc.out + off * 48 : ctx->d_stage_out + slot * ch * 96;
+            int32_t *d_st = dc.sums ? dc.status + off : ctx->d_status + slot * ch;
+            RC(commit_chunk(ctx, ctx->d_stage_in + slot * ch * bpb, cnt, d_out, d_st, off, &dc));
+            if (!dc.sums) {
+                CU(cudaMemcpyAsync(out + off * 48, d_out, cnt * 48, cudaMemcpyDeviceToHost, ctx->cur->stream));
+                CU(cudaMemcpyAsync(status + off, d_st, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->cur->stream));
+            }
+            return KZG_B200_OK;
+        },
+        [&]() -> int {
+            if (!dc.sums) return KZG_B200_OK;
+            RC(deferred_finish(ctx, &dc, dc.status, dc.out));
+            CU(cudaMemcpyAsync(out, dc.out, n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(status, dc.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
             return KZG_B200_OK;
         });
 }

@@ -114,6 +114,8 @@ extern "C" int kzg_b200_compute_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const ui
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     const size_t bpb = (size_t)ctx->n * 32, ch = ctx->chunk;
+    DeferredCompress dc;
+    RC(deferred_begin(ctx, n, &dc));
     return staged_chunks(
         ctx, n,
         [&](int slot, size_t off, size_t cnt) -> int {
@@ -122,11 +124,21 @@ extern "C" int kzg_b200_compute_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const ui
             return KZG_B200_OK;
         },
         [&](int slot, size_t off, size_t cnt) -> int {
-            uint8_t *d_out = ctx->d_stage_out + slot * ch * 96;
-            int32_t *d_st = ctx->d_status + slot * ch;
-            RC(proof_chunk(ctx, ctx->d_stage_in + slot * ch * bpb, ctx->d_stage_aux + slot * ch * 96, nullptr, cnt, d_out, nullptr, d_st));
-            CU(cudaMemcpyAsync(proofs_out + off * 48, d_out, cnt * 48, cudaMemcpyDeviceToHost, ctx->cur->stream));
-            CU(cudaMemcpyAsync(status + off, d_st, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->cur->stream));
+            uint8_t *d_out = dc.sums ? dc.out + off * 48 : ctx->d_stage_out + slot * ch * 96;
+            int32_t *d_st = dc.sums ? dc.status + off : ctx->d_status + slot * ch;
+            RC(proof_chunk(ctx, ctx->d_stage_in + slot * ch * bpb, ctx->d_stage_aux + slot * ch * 96, nullptr, cnt, d_out, nullptr, d_st,
+                           nullptr, off, &dc));
+            if (!dc.sums) {
+                CU(cudaMemcpyAsync(proofs_out + off * 48, d_out, cnt * 48, cudaMemcpyDeviceToHost, ctx->cur->stream));
+                CU(cudaMemcpyAsync(status + off, d_st, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->cur->stream));
+            }
+            return KZG_B200_OK;
+        },
+        [&]() -> int {
+            if (!dc.sums) return KZG_B200_OK;
+            RC(deferred_finish(ctx, &dc, dc.status, dc.out));
+            CU(cudaMemcpyAsync(proofs_out, dc.out, n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(status, dc.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
             return KZG_B200_OK;
         });
 }
