@@ -101,8 +101,13 @@ struct kzg_b200_ctx {
     size_t sums_all_elems = 0;
     kzg::fr_t *d_z_all = nullptr;          // challenges of a whole device-resident call (grow-only)
     size_t z_all_elems = 0;
-    uint8_t *d_vb = nullptr;          // phase-B buffer of batch verification (grow-only)
+    uint8_t *d_vb = nullptr;          // buffers of one verification call (grow-only)
     size_t vb_bytes = 0;
+    // what the last kzg_b200_verify_phase_a validated and left decoded in d_vb: SHA-256 over (n, commitments, proofs).
+    // kzg_b200_verify_phase_b on the same bytes reuses the decoded points instead of validating them again.
+    bool va_valid = false;
+    size_t va_n = 0;
+    uint8_t va_digest[32];
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
     // optional per-stage device timing (CUDA events on `stream`), see kzg_b200_profile_*

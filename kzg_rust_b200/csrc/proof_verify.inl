@@ -187,7 +187,8 @@ struct VerifyBufs {
     fr_t *sy;              // n + 1
     uint8_t *partial;      // 256
 };
-static int verify_bufs(kzg_b200_ctx *ctx, size_t n, VerifyBufs *vb) {
+static int verify_bufs(kzg_b200_ctx *ctx, size_t n, VerifyBufs *vb, bool keep_phase_a = false) {
+    if (!keep_phase_a) ctx->va_valid = false;  // the buffers are about to be rewritten
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
     const size_t o_pts = 0, o_zy = o_pts + up(2 * n * sizeof(g1_affine_t)), o_in = o_zy + up(64 * n), o_st = o_in + up(96 * n),
                  o_terms = o_st + up(2 * n * sizeof(int32_t)), o_partials = o_terms + up(3 * n * sizeof(g1_jac_t)),
@@ -270,12 +271,27 @@ static int verify_phase_a_locked(kzg_b200_ctx *ctx, const uint8_t *blobs, const 
         if (st[i] != KZG_B200_OK) return KZG_B200_BAD_ARGS;
     return KZG_B200_OK;
 }
+static void points_digest(uint8_t out[32], const uint8_t *commitments, const uint8_t *proofs, size_t n) {
+    HostSha256 h;
+    h.init();
+    uint64_t n64 = n;
+    h.update(reinterpret_cast<const uint8_t *>(&n64), 8);
+    h.update(commitments, 48 * n);
+    h.update(proofs, 48 * n);
+    h.finish(out);
+}
 extern "C" int kzg_b200_verify_phase_a(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *commitments,
                                        const uint8_t *proofs, size_t n, uint8_t *zy_out) {
     if (!ctx || (n && (!blobs || !commitments || !proofs || !zy_out))) return KZG_B200_BAD_ARGS;
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(cudaSetDevice(ctx->device));
-    return verify_phase_a_locked(ctx, blobs, commitments, proofs, n, zy_out);
+    RC(verify_phase_a_locked(ctx, blobs, commitments, proofs, n, zy_out));
+    if (n) {  // every point passed validation and sits decoded in the context's buffers: remember which bytes they were
+        points_digest(ctx->va_digest, commitments, proofs, n);
+        ctx->va_n = n;
+        ctx->va_valid = true;
+    }
+    return KZG_B200_OK;
 }
 
 // reference compute_r_powers (src/utils.rs:426-474), the hash only: the points are hashed in
@@ -331,6 +347,8 @@ static void empty_partial(uint8_t partial_out[224]) {
 }
 // Phase B from host bytes: nothing is assumed about them -- the points are decompressed AND subgroup-checked here,
 // z_i and y_i must be canonical (a caller may run phase B on another context, or on re-fetched data, than phase A).
+// The one shortcut: when the commitment and proof bytes are exactly the ones this context's last phase A validated
+// (same SHA-256), their decoded points are still in the context's buffers and are used as they are.
 static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, const uint8_t *zy, const uint8_t *proofs,
                                  size_t n, const uint8_t r[32], uint64_t first_index, uint8_t partial_out[224]) {
     if (n == 0) { empty_partial(partial_out); return KZG_B200_OK; }
@@ -339,12 +357,19 @@ static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, 
         scalar_from_be32(t, zy + 32 * i);
         if (!fr_is_canonical(t)) return KZG_B200_BAD_ARGS;  // bytes_to_bls_field, src/utils.rs:262-275
     }
+    bool reuse = false;
+    if (ctx->va_valid && ctx->va_n == n) {
+        uint8_t dg[32];
+        points_digest(dg, commitments, proofs, n);
+        reuse = memcmp(dg, ctx->va_digest, 32) == 0;
+    }
     VerifyBufs vb;
-    RC(verify_bufs(ctx, n, &vb));
+    RC(verify_bufs(ctx, n, &vb, reuse));
     ctx->cur = &ctx->lanes[0];
+    CU(cudaMemcpyAsync(vb.zy, zy, 64 * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (reuse) return verify_phase_b_device(ctx, vb, n, n, r, first_index, partial_out);
     CU(cudaMemcpyAsync(vb.in_bytes, commitments, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(vb.in_bytes + 48 * n, proofs, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(vb.zy, zy, 64 * n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(vb.status, 0, n * sizeof(int32_t), ctx->stream));
     stage_begin(ctx, KZG_B200_STAGE_VALIDATE);
     int rc = g1_launch_decode2(ctx->stream, vb.in_bytes, vb.in_bytes + 48 * n, vb.pts, vb.pts + n, vb.status, n, 1);

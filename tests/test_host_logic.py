@@ -416,3 +416,46 @@ def test_paired_multiplication_vs_python(field):
         a1, b1, a2, b2 = vals[i], vals[i + 1], vals[i + 2], vals[i + 3]
         field.shim_fp_mul2(_limbs(a1, 12), _limbs(b1, 12), _limbs(a2, 12), _limbs(b2, 12), r1, r2)
         assert _val(r1) == a1 * b1 * Rp_inv % P and _val(r2) == a2 * b2 * Rp_inv % P
+
+
+def test_host_verify_finish_on_records_built_from_the_public_tau():
+    """kzg_b200_verify_finish (the host end of batch verification, reference src/kzg.rs:618-625): partial records
+    (A, B, s) with B - [s]G1 = [tau]A must be accepted, anything else rejected.  tau = 1337 for the bundled testing setup, so
+    the records can be made with the oracle's G1 arithmetic alone: A = [a]G1, B = [1337 a + s]G1, split over shards."""
+    import kzg_rust_b200 as k
+    from oracle import binding as ob
+    L = k.load_library()
+    L.kzg_b200_host_verify_finish_with_tau.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int)]
+    g = golden()
+    tau_g2 = g.g2_bytes[96:192]
+    gen = bytes.fromhex("97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb")
+
+    def point(scalar):  # [scalar]G1 as the 96-byte uncompressed record of the partial format
+        c = ob.g1_lincomb([gen], [(scalar % R).to_bytes(32, "big")])
+        if c[0] & 0x40:
+            return bytes([0x40]) + bytes(95)
+        x = int.from_bytes(bytes([c[0] & 0x1f]) + c[1:], "big")
+        y = pow((x ** 3 + 4) % P, (P + 1) // 4, P)
+        if (y > (P - 1) // 2) != bool(c[0] & 0x20):
+            y = P - y
+        return x.to_bytes(48, "big") + y.to_bytes(48, "big")
+
+    rng = np.random.default_rng(77)
+    for shards in (1, 3):
+        recs, good = b"", True
+        for _ in range(shards):
+            a = int.from_bytes(rng.bytes(32), "big") % R
+            s_ = int.from_bytes(rng.bytes(32), "big") % R
+            recs += point(a) + point(1337 * a + s_) + s_.to_bytes(32, "big")
+        ok = ctypes.c_int(-1)
+        assert L.kzg_b200_host_verify_finish_with_tau(tau_g2, recs, shards, ctypes.byref(ok)) == 0 and ok.value == 1
+        bad = bytearray(recs)
+        bad[192 + 31] ^= 1  # another s
+        assert L.kzg_b200_host_verify_finish_with_tau(tau_g2, bytes(bad), shards, ctypes.byref(ok)) == 0 and ok.value == 0
+    # empty sums and s = 0: e(inf, .) == e(inf, .)
+    rec = bytes([0x40]) + bytes(95) + bytes([0x40]) + bytes(95) + bytes(32)
+    ok = ctypes.c_int(-1)
+    assert L.kzg_b200_host_verify_finish_with_tau(tau_g2, rec, 1, ctypes.byref(ok)) == 0 and ok.value == 1
+    # a scalar that is not canonical is malformed
+    rec = bytes([0x40]) + bytes(95) + bytes([0x40]) + bytes(95) + b"\xff" * 32
+    assert L.kzg_b200_host_verify_finish_with_tau(tau_g2, rec, 1, ctypes.byref(ok)) != 0
