@@ -142,8 +142,11 @@ static int ctx_init(kzg_b200_ctx *ctx, const uint8_t *g1_lagrange, size_t n1, co
     }
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
+    // KZG_B200_MEM_BUDGET_GB: plan as if only this much device memory were free (a GPU shared with other tenants; tests)
+    const size_t budget = (size_t)std::max(0, env_int("KZG_B200_MEM_BUDGET_GB", 0)) << 30;
+    if (budget && budget < free_b) free_b = budget;
     const size_t chunk_cap = (size_t)std::max(1, env_int("KZG_B200_CHUNK", 4096));
-    const size_t reserve = (size_t)8 << 30;  // left for the caller's device-resident blobs
+    const size_t reserve = std::min((size_t)8 << 30, free_b / 8);  // left for the caller's device-resident blobs
     int g = comb_width > 0 ? comb_width : env_int("KZG_B200_COMB_WIDTH", 0);
     if (g <= 0) {
         // The widest comb whose table (a) takes at most half of the free device memory and (b) still leaves room for
@@ -169,6 +172,7 @@ static int ctx_init(kzg_b200_ctx *ctx, const uint8_t *g1_lagrange, size_t n1, co
     RC(fr_setup_roots_device(ctx->n, &ctx->d_roots, ctx->stream));
     // workspace: as many blobs per chunk as memory allows, capped (KZG_B200_CHUNK overrides)
     CU(cudaMemGetInfo(&free_b, &total_b));
+    if (budget) free_b = std::min(free_b, budget > table_bytes(n1, g) ? budget - table_bytes(n1, g) : (size_t)0);
     const size_t fixed = scratch_bytes(ctx) + reserve;
     const size_t usable = free_b > fixed + ((size_t)1 << 30) ? free_b - fixed : free_b / 2;
     const size_t chunk = std::max<size_t>(1, std::min(chunk_cap, usable / per_blob_workspace(ctx)));

@@ -223,3 +223,27 @@ def test_trusted_setup_json_to_settings():
     out = k.Kzg.blob_to_kzg_commitment(k.Blob.from_bytes(G.get_bytes(case["input"]["blob"])), s)
     assert "0x" + out.to_bytes().hex() == case["output"]
     s.close()
+
+
+def test_automatic_comb_width_follows_the_memory_rule():
+    """comb_width = 0: the widest comb whose table takes at most half of the free memory and leaves room for a workspace
+    and the reserve (include/kzg_b200.h); on a small or shared GPU the width steps down, it never collapses to a tiny
+    window, and the bytes stay the same."""
+    k = _kzg()
+    case = next(c for c in G.by_fn("blob_to_kzg_commitment") if c["output"] is not None)
+    widths = []
+    for budget_gb in (160, 60, 24, 9):
+        os.environ["KZG_B200_MEM_BUDGET_GB"] = str(budget_gb)
+        try:
+            s = k.KzgSettings.load_trusted_setup(G.g1_bytes, G.g2_bytes, 0, 0)
+        finally:
+            del os.environ["KZG_B200_MEM_BUDGET_GB"]
+        widths.append(s.comb_width)
+        assert s.table_bytes <= budget_gb * 2 ** 30 // 2 and s.chunk_blobs >= 1, (budget_gb, s.comb_width, s.table_bytes)
+        # one step wider would not have fitted in half of the budget
+        wider = -(-4096 // (s.comb_width + 1)) * 2 ** s.comb_width * 96
+        assert s.comb_width == 24 or wider > budget_gb * 2 ** 30 // 2 or budget_gb < 16, (budget_gb, s.comb_width)
+        out = k.Kzg.blob_to_kzg_commitment(k.Blob.from_bytes(G.get_bytes(case["input"]["blob"])), s)
+        assert "0x" + out.to_bytes().hex() == case["output"]
+        s.close()
+    assert widths[0] == 23 and widths == sorted(widths, reverse=True) and widths[-1] >= 12, widths
