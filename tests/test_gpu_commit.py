@@ -232,7 +232,10 @@ def test_automatic_comb_width_follows_the_memory_rule():
     k = _kzg()
     case = next(c for c in G.by_fn("blob_to_kzg_commitment") if c["output"] is not None)
     widths = []
+    import torch
     for budget_gb in (160, 60, 24, 9):
+        # other contexts of this test session hold memory too: the rule plans with min(budget, what is free now)
+        eff = min(budget_gb * 2 ** 30, torch.cuda.mem_get_info(0)[0])
         os.environ["KZG_B200_MEM_BUDGET_GB"] = str(budget_gb)
         try:
             s = k.KzgSettings.load_trusted_setup(G.g1_bytes, G.g2_bytes, 0, 0)
@@ -242,8 +245,8 @@ def test_automatic_comb_width_follows_the_memory_rule():
         assert s.table_bytes <= budget_gb * 2 ** 30 // 2 and s.chunk_blobs >= 1, (budget_gb, s.comb_width, s.table_bytes)
         # one step wider would not have fitted in half of the budget
         wider = -(-4096 // (s.comb_width + 1)) * 2 ** s.comb_width * 96
-        assert s.comb_width == 24 or wider > budget_gb * 2 ** 30 // 2 or budget_gb < 16, (budget_gb, s.comb_width)
+        assert s.comb_width == 24 or wider > eff // 2 or eff < 16 * 2 ** 30, (budget_gb, eff, s.comb_width)
         out = k.Kzg.blob_to_kzg_commitment(k.Blob.from_bytes(G.get_bytes(case["input"]["blob"])), s)
         assert "0x" + out.to_bytes().hex() == case["output"]
         s.close()
-    assert widths[0] == 23 and widths == sorted(widths, reverse=True) and widths[-1] >= 12, widths
+    assert widths == sorted(widths, reverse=True) and widths[-1] >= 12, widths
