@@ -4,6 +4,7 @@
 
 #include "internal.h"
 #include "frpath.cuh"
+#include "pippenger.cuh"
 
 using namespace kzg;
 
@@ -53,6 +54,44 @@ int fr_launch_verify_sums(cudaStream_t st, const g1_jac_t *d_terms, const fr_t *
     } else {
         k_jac_sum<<<2, KZG_JSUM_THREADS, 0, st>>>(d_terms, n, 2 * n, d_sums);
     }
+    k_fr_sum<<<1, 256, 0, st>>>(d_sy, n, d_sy_total);
+    k_write_partial<<<1, 32, 0, st>>>(d_sums, d_sy_total, d_partial);
+    CU(cudaGetLastError());
+    return KZG_B200_OK;
+}
+
+// The same sums by the bucket method (pippenger.cuh): sy[i] = r_i y_i, then rows[o * pl.rows + p] = 2^p S_p of output o;
+// fr_launch_verify_sums_rows adds them.  d_ws: fr_pip_workspace_bytes(count) bytes, 256-byte aligned.
+size_t fr_pip_workspace_bytes(size_t count) {
+    // the entry lists are longest at c = 1 (129 windows), the bucket arrays largest at c = KZG_PIP_MAX_C
+    const PipPlan small = PipPlan::make(count, 1), big = PipPlan::make(count, KZG_PIP_MAX_C);
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    return up(16 * sizeof(uint32_t) * count) + 3 * up((big.buckets + 1) * sizeof(uint32_t)) + up(small.max_entries * sizeof(uint32_t)) +
+           up(big.buckets * sizeof(g1_jac_t)) + up(2 * (size_t)KZG_PIP_SCALAR_BITS * sizeof(g1_jac_t));
+}
+int fr_launch_verify_pippenger(cudaStream_t st, const g1_affine_t *d_cpts, const g1_affine_t *d_ppts, const uint8_t *d_zy,
+                               const fr_t &r_canon, uint64_t first, size_t count, int force_c, uint8_t *d_ws, fr_t *d_sy,
+                               g1_affine_t *d_sums, fr_t *d_sy_total, uint8_t *d_partial) {
+    if (count == 0 || count > KZG_PIP_IDX) return KZG_B200_BAD_ARGS;
+    const PipPlan pl = PipPlan::make(count, force_c), big = PipPlan::make(count, KZG_PIP_MAX_C), small = PipPlan::make(count, 1);
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    uint32_t *halves = reinterpret_cast<uint32_t *>(d_ws);
+    uint32_t *counts = reinterpret_cast<uint32_t *>(d_ws + up(16 * sizeof(uint32_t) * count));
+    uint32_t *offsets = counts + up((big.buckets + 1) * sizeof(uint32_t)) / sizeof(uint32_t);
+    uint32_t *cursor = offsets + up((big.buckets + 1) * sizeof(uint32_t)) / sizeof(uint32_t);
+    uint32_t *entries = cursor + up((big.buckets + 1) * sizeof(uint32_t)) / sizeof(uint32_t);
+    g1_jac_t *buckets = reinterpret_cast<g1_jac_t *>(reinterpret_cast<uint8_t *>(entries) + up(small.max_entries * sizeof(uint32_t)));
+    g1_jac_t *rows = reinterpret_cast<g1_jac_t *>(reinterpret_cast<uint8_t *>(buckets) + up(big.buckets * sizeof(g1_jac_t)));
+    const uint32_t n = (uint32_t)count;
+    CU(cudaMemsetAsync(counts, 0, pl.buckets * sizeof(uint32_t), st));
+    k_pip_scalars<<<blocks_for(count, 64), 64, 0, st>>>(d_zy, r_canon, first, n, halves, d_sy);
+    const uint64_t dt = (uint64_t)count * pl.W;
+    k_pip_digits<false><<<blocks_for(dt, 128), 128, 0, st>>>(pl, n, halves, counts, nullptr);
+    k_pip_scan<<<1, 1024, 0, st>>>(counts, pl.buckets, offsets, cursor);
+    k_pip_digits<true><<<blocks_for(dt, 128), 128, 0, st>>>(pl, n, halves, cursor, entries);
+    k_pip_buckets<<<blocks_for(pl.buckets, 64), 64, 0, st>>>(pl, offsets, entries, d_cpts, d_ppts, buckets);
+    k_pip_rows<<<2 * pl.rows, KZG_PIP_ROW_THREADS, 0, st>>>(pl, buckets, rows);
+    k_jac_sum<<<2, KZG_JSUM_THREADS, 0, st>>>(rows, pl.rows, pl.rows, d_sums);
     k_fr_sum<<<1, 256, 0, st>>>(d_sy, n, d_sy_total);
     k_write_partial<<<1, 32, 0, st>>>(d_sums, d_sy_total, d_partial);
     CU(cudaGetLastError());

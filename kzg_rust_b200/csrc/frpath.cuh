@@ -200,12 +200,16 @@ __global__ void __launch_bounds__(128) k_challenge_warp(const uint8_t *__restric
             uint32_t a = h[0], bb = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
 #pragma unroll
             for (int t = 0; t < 64; t++) {
-                uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
-                uint32_t ch = (e & f) ^ (~e & g);
-                uint32_t t1 = hh + mine[t * 32 + i] + S1 + ch;
-                uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
-                uint32_t mj = (a & bb) ^ (a & c) ^ (bb & c);
-                hh = g; g = f; f = e; e = d + t1; d = c; c = bb; bb = a; a = t1 + S0 + mj;
+                // One warp runs one dependent chain, so the depth of a round is what counts: h + K + W and d + h + K + W
+                // do not depend on this round's e, which leaves rotate -> xor -> ONE three-input add on the path from
+                // e to the next e (and from a to the next a), where the textbook order has three adds.
+                const uint32_t hkw = hh + mine[t * 32 + i], dhkw = d + hkw;
+                const uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
+                const uint32_t ch = (e & f) ^ (~e & g);
+                const uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
+                const uint32_t mj = (a & bb) ^ (a & c) ^ (bb & c);
+                const uint32_t t1 = hkw + S1 + ch;
+                hh = g; g = f; f = e; e = dhkw + S1 + ch; d = c; c = bb; bb = a; a = t1 + S0 + mj;
             }
             h[0] += a; h[1] += bb; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
         }

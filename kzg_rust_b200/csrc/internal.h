@@ -163,6 +163,12 @@ int fr_launch_eval(cudaStream_t st, int quotient, const uint8_t *d_blobs, const 
                    kzg::fr_t *d_inv, kzg::fr_t *d_poly, uint8_t *d_zy, int32_t *d_status, size_t count);
 int fr_launch_verify_terms(cudaStream_t st, const kzg::g1_affine_t *d_cpts, const kzg::g1_affine_t *d_ppts, const uint8_t *d_zy,
                            const kzg::fr_t &r_canon, uint64_t first, size_t count, kzg::g1_jac_t *d_terms, kzg::fr_t *d_sy);
+// the same three sums by the bucket method (pippenger.cuh), down to the 224-byte partial record: 9 kernels
+#define KZG_PIP_LAUNCHES 9
+size_t fr_pip_workspace_bytes(size_t count);
+int fr_launch_verify_pippenger(cudaStream_t st, const kzg::g1_affine_t *d_cpts, const kzg::g1_affine_t *d_ppts, const uint8_t *d_zy,
+                               const kzg::fr_t &r_canon, uint64_t first, size_t count, int force_c, uint8_t *d_ws, kzg::fr_t *d_sy,
+                               kzg::g1_affine_t *d_sums, kzg::fr_t *d_sy_total, uint8_t *d_partial);
 #define KZG_VERIFY_SUM_BLOCKS 148
 int fr_launch_verify_sums(cudaStream_t st, const kzg::g1_jac_t *d_terms, const kzg::fr_t *d_sy, size_t count,
                           kzg::g1_affine_t *d_sums, kzg::fr_t *d_sy_total, uint8_t *d_partial, kzg::g1_jac_t *d_partials);

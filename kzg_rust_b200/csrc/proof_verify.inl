@@ -186,6 +186,7 @@ struct VerifyBufs {
     g1_affine_t *sums;     // 2
     fr_t *sy;              // n + 1
     uint8_t *partial;      // 256
+    uint8_t *pip;          // workspace of the bucket method (fr_pip_workspace_bytes)
 };
 static int verify_bufs(kzg_b200_ctx *ctx, size_t n, VerifyBufs *vb, bool keep_phase_a = false) {
     if (!keep_phase_a) ctx->va_valid = false;  // the buffers are about to be rewritten
@@ -193,7 +194,7 @@ static int verify_bufs(kzg_b200_ctx *ctx, size_t n, VerifyBufs *vb, bool keep_ph
     const size_t o_pts = 0, o_zy = o_pts + up(2 * n * sizeof(g1_affine_t)), o_in = o_zy + up(64 * n), o_st = o_in + up(96 * n),
                  o_terms = o_st + up(2 * n * sizeof(int32_t)), o_partials = o_terms + up(3 * n * sizeof(g1_jac_t)),
                  o_sums = o_partials + up(2 * KZG_VERIFY_SUM_BLOCKS * sizeof(g1_jac_t)), o_sy = o_sums + up(2 * sizeof(g1_affine_t)),
-                 o_part = o_sy + up((n + 1) * sizeof(fr_t)), total = o_part + 256;
+                 o_part = o_sy + up((n + 1) * sizeof(fr_t)), o_pip = o_part + 256, total = o_pip + fr_pip_workspace_bytes(n);
     if (total > ctx->vb_bytes) {
         if (ctx->d_vb) CU(cudaFree(ctx->d_vb));
         ctx->d_vb = nullptr;
@@ -204,7 +205,7 @@ static int verify_bufs(kzg_b200_ctx *ctx, size_t n, VerifyBufs *vb, bool keep_ph
     uint8_t *d = ctx->d_vb;
     vb->pts = (g1_affine_t *)(d + o_pts); vb->zy = d + o_zy; vb->in_bytes = d + o_in; vb->status = (int32_t *)(d + o_st);
     vb->terms = (g1_jac_t *)(d + o_terms); vb->partials = (g1_jac_t *)(d + o_partials); vb->sums = (g1_affine_t *)(d + o_sums);
-    vb->sy = (fr_t *)(d + o_sy); vb->partial = d + o_part;
+    vb->sy = (fr_t *)(d + o_sy); vb->partial = d + o_part; vb->pip = d + o_pip;
     return KZG_B200_OK;
 }
 
@@ -330,10 +331,20 @@ static int verify_phase_b_device(kzg_b200_ctx *ctx, const VerifyBufs &vb, size_t
     if (!fr_is_canonical(rc)) return KZG_B200_BAD_ARGS;
     ctx->cur = &ctx->lanes[0];
     stage_begin(ctx, KZG_B200_STAGE_VERIFY_TERMS);
-    int lrc = fr_launch_verify_terms(ctx->stream, vb.pts, vb.pts + n_stride, vb.zy, rc, first_index, n, vb.terms, vb.sy);
-    if (lrc == KZG_B200_OK) lrc = fr_launch_verify_sums(ctx->stream, vb.terms, vb.sy, n, vb.sums, vb.sy + n, vb.partial, vb.partials);
-    stage_end(ctx, 5);
-    ctx->launches += 5;
+    // KZG_B200_VERIFY_LADDER=1: one GLV ladder per term (k_verify_terms) instead of the bucket method -- the
+    // independent path the tests compare the partial records with.  KZG_B200_PIP_C: force the window width.
+    int lrc, nl;
+    if (env_int("KZG_B200_VERIFY_LADDER", 0)) {
+        lrc = fr_launch_verify_terms(ctx->stream, vb.pts, vb.pts + n_stride, vb.zy, rc, first_index, n, vb.terms, vb.sy);
+        if (lrc == KZG_B200_OK) lrc = fr_launch_verify_sums(ctx->stream, vb.terms, vb.sy, n, vb.sums, vb.sy + n, vb.partial, vb.partials);
+        nl = 5;
+    } else {
+        lrc = fr_launch_verify_pippenger(ctx->stream, vb.pts, vb.pts + n_stride, vb.zy, rc, first_index, n, env_int("KZG_B200_PIP_C", 0),
+                                         vb.pip, vb.sy, vb.sums, vb.sy + n, vb.partial);
+        nl = KZG_PIP_LAUNCHES;
+    }
+    stage_end(ctx, nl);
+    ctx->launches += nl;
     RC(lrc);
     CU(cudaMemcpyAsync(partial_out, vb.partial, 224, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));

@@ -140,3 +140,76 @@ extern "C" int shim_g1_mul_both(const uint8_t *point48, const uint32_t *k, uint8
     glv_split(k1k2, k1k2 + 4, k);
     return 0;
 }
+
+// Phase B of batch verification on the CPU, twice: the bucket method of pippenger.cuh walked thread by thread
+// (scalars -> count -> offsets -> scatter -> bucket sums -> weighted rows -> total) and one GLV ladder per term.
+// Points come compressed (48 B each); out_* = A (48 B compressed) || B (48 B) || sum r_i y_i (32 B little-endian limbs).
+#include "../../kzg_rust_b200/csrc/pippenger.cuh"
+extern "C" int shim_verify_sums(const uint8_t *commitments, const uint8_t *proofs, const uint8_t *zy, const uint8_t *r_be, uint64_t first,
+                                int n, int force_c, uint8_t *out_pip, uint8_t *out_ladder, int *c_used) {
+    std::vector<g1_affine_t> cp(n), pp(n);
+    for (int i = 0; i < n; i++)
+        if (!g1a_uncompress(cp[i], commitments + 48 * i) || !g1a_uncompress(pp[i], proofs + 48 * i)) return KZG_BADARGS;
+    fr_t r;
+    scalar_from_be32(r, r_be);
+    const PipPlan pl = PipPlan::make((size_t)n, force_c);
+    *c_used = pl.c;
+    std::vector<uint32_t> halves(16 * (size_t)n), counts(pl.buckets, 0), offsets(pl.buckets + 1), cursor(pl.buckets), entries(pl.max_entries);
+    std::vector<fr_t> sy(n);
+    for (int i = 0; i < n; i++) pip_scalars_thread((uint32_t)i, zy, r, first, halves.data(), sy.data());
+    for (int w = 0; w < pl.W; w++)
+        for (int i = 0; i < n; i++) pip_digits_thread<false>((uint32_t)i, w, pl, halves.data(), counts.data(), nullptr);
+    uint32_t run = 0;
+    for (uint32_t b = 0; b < pl.buckets; b++) { offsets[b] = cursor[b] = run; run += counts[b]; }
+    offsets[pl.buckets] = run;
+    if (run > pl.max_entries) return KZG_INTERNAL;
+    for (int w = 0; w < pl.W; w++)
+        for (int i = 0; i < n; i++) pip_digits_thread<true>((uint32_t)i, w, pl, halves.data(), cursor.data(), entries.data());
+    std::vector<g1_jac_t> buckets(pl.buckets);
+    for (uint32_t b = 0; b < pl.buckets; b++) pip_bucket_thread(b, pl, offsets.data(), entries.data(), cp.data(), pp.data(), buckets.data());
+    fr_t s_tot;
+    fe_set_zero(s_tot);
+    for (int i = 0; i < n; i++) fe_add(s_tot, s_tot, sy[i]);
+    fe_from_mont(s_tot, s_tot);
+    for (int o = 0; o < 2; o++) {
+        g1_jac_t total;
+        g1j_set_inf(total);
+        for (uint32_t p = 0; p < pl.rows; p++) {
+            const int w = (int)(p / pl.c), j = (int)(p % pl.c);
+            g1_jac_t row;
+            g1j_set_inf(row);
+            for (uint32_t t = 0; t < pip_row_len(pl, o, w, j); t++) g1j_add(row, row, buckets[pip_row_slot(pl, o, w, j, t)]);
+            pip_weight(row, p);
+            g1j_add(total, total, row);
+        }
+        g1_affine_t a;
+        g1j_to_affine(a, total);
+        g1a_compress(out_pip + 48 * o, a);
+    }
+    memcpy(out_pip + 96, s_tot.l, 32);
+    // the ladders
+    fr_t rm, s2;
+    fe_to_mont(rm, r);
+    fe_set_zero(s2);
+    g1_jac_t A, B;
+    g1j_set_inf(A);
+    g1j_set_inf(B);
+    for (int i = 0; i < n; i++) {
+        fr_t ri, y, z, k;
+        fr_pow_u64(ri, rm, first + (uint64_t)i);
+        scalar_from_be32(y, zy + 64 * (size_t)i + 32); fe_to_mont(y, y); fe_mul(y, ri, y); fe_add(s2, s2, y);
+        scalar_from_be32(z, zy + 64 * (size_t)i); fe_to_mont(z, z); fe_mul(z, ri, z);
+        g1_jac_t t;
+        fe_from_mont(k, ri);
+        g1j_mul(t, pp[i], k.l, 255); g1j_add(A, A, t);
+        g1j_mul(t, cp[i], k.l, 255); g1j_add(B, B, t);
+        fe_from_mont(k, z);
+        g1j_mul(t, pp[i], k.l, 255); g1j_add(B, B, t);
+    }
+    g1_affine_t a;
+    g1j_to_affine(a, A); g1a_compress(out_ladder, a);
+    g1j_to_affine(a, B); g1a_compress(out_ladder + 48, a);
+    fe_from_mont(s2, s2);
+    memcpy(out_ladder + 96, s2.l, 32);
+    return 0;
+}

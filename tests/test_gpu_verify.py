@@ -350,3 +350,49 @@ def test_one_context_from_several_host_threads():
         blobs, cms, proofs = sets[t]
         for c, p, st, ok, nok in results[t]:
             assert c == cms.tobytes() and p == proofs.tobytes() and not st and ok is True and nok is False
+
+
+@pytest.mark.parametrize("n", [1, 2, 6, 11, 64, 300, 1024, 5000])
+def test_phase_b_bucket_method_equals_the_ladders(n):
+    """The bucket method (csrc/pippenger.cuh, the default) and one GLV ladder per term (KZG_B200_VERIFY_LADDER=1) give
+    byte-identical 224-byte partial records for every window width the size rule picks and for forced ones; a
+    shard's first index enters the powers.  Points at infinity and repeated points are in the batch."""
+    k = _kzg()
+    L = k.load_library()
+    s = gpu_settings("mainnet", 8)
+    m = min(n, 64)
+    blobs, cms, proofs = _make_batch(k, s, m, 4000 + n)
+    zy_small = np.zeros((m, 64), dtype=np.uint8)
+    assert L.kzg_b200_verify_phase_a(s._h, blobs.ctypes.data, cms.ctypes.data, proofs.ctypes.data, m, zy_small.ctypes.data) == 0
+    # phase B is a function of (C, z, y, proof) records alone: tile the valid records up to n
+    rng = np.random.default_rng(n)
+    pick = rng.integers(0, m, size=n) if n > m else np.arange(n)
+    cm, pr, zy = cms[pick].copy(), proofs[pick].copy(), zy_small[pick].copy()
+    zy[:, :] = np.frombuffer(b"".join((int.from_bytes(rng.bytes(32), "big") % R).to_bytes(32, "big") for _ in range(2 * n)),
+                             dtype=np.uint8).reshape(n, 64)
+    inf = np.frombuffer(b"\xc0" + bytes(47), dtype=np.uint8)
+    if n >= 6:
+        cm[1] = inf
+        pr[2] = inf
+        pr[4] = cm[4]
+        zy[3, :32] = 0
+    r = np.frombuffer((int.from_bytes(rng.bytes(32), "big") % R).to_bytes(32, "big"), dtype=np.uint8).copy()
+
+    def partial(first, **env):
+        out = np.zeros(224, dtype=np.uint8)
+        for key, v in env.items():
+            os.environ[key] = str(v)
+        try:
+            rc = L.kzg_b200_verify_phase_b(s._h, cm.ctypes.data, zy.ctypes.data, pr.ctypes.data, n, r.ctypes.data, first, out.ctypes.data)
+        finally:
+            for key in env:
+                del os.environ[key]
+        assert rc == 0
+        return out.tobytes()
+
+    for first in (0, 77):
+        want = partial(first, KZG_B200_VERIFY_LADDER=1)
+        assert partial(first) == want
+        for c in (1, 2, 5, 9, 12):
+            if n <= 300 or c >= 5:
+                assert partial(first, KZG_B200_PIP_C=c) == want, (n, first, c)

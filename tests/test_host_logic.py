@@ -459,3 +459,38 @@ def test_host_verify_finish_on_records_built_from_the_public_tau():
     # a scalar that is not canonical is malformed
     rec = bytes([0x40]) + bytes(95) + bytes([0x40]) + bytes(95) + b"\xff" * 32
     assert L.kzg_b200_host_verify_finish_with_tau(tau_g2, rec, 1, ctypes.byref(ok)) != 0
+
+
+@pytest.mark.parametrize("n,force_c", [(1, 0), (3, 0), (6, 0), (6, 3), (13, 2), (40, 0), (40, 5), (9, 12)])
+def test_bucket_method_of_phase_b_vs_ladders(msm, n, force_c):
+    """pippenger.cuh walked on the CPU (GLV halves, Booth digits, counting sort, bucket sums, bit-position rows,
+    weights) against one plain 255-step ladder per term, and against Python integers for the scalar sum: every
+    window width, points at infinity, repeated points, z = 0, r = 1 and r^i z_i that make digits cancel."""
+    g = golden()
+    rng = np.random.default_rng(100 + n + force_c)
+    inf = b"\xc0" + bytes(47)
+    pts = [g.g1_bytes[48 * i:48 * i + 48] for i in rng.integers(0, 4096, size=2 * n)]
+    cms, prs = pts[:n], pts[n:]
+    if n >= 3:
+        cms[1] = inf
+        prs[2] = inf
+        prs[0] = cms[0]           # the same point in two lanes
+    if n >= 6:
+        cms[4] = cms[3]           # equal points inside one lane: a bucket meets P + P
+    zs = [int.from_bytes(rng.bytes(32), "big") % R for _ in range(n)]
+    ys = [int.from_bytes(rng.bytes(32), "big") % R for _ in range(n)]
+    zs[0] = 0
+    if n >= 6:
+        zs[3], zs[5] = 1, R - 1
+    zy = b"".join(z.to_bytes(32, "big") + y.to_bytes(32, "big") for z, y in zip(zs, ys))
+    for r, first in ((int.from_bytes(rng.bytes(32), "big") % R, 0), (1, 0), (R - 1, 5), (int.from_bytes(rng.bytes(32), "big") % R, 12345)):
+        a, b = (ctypes.c_uint8 * 128)(), (ctypes.c_uint8 * 128)()
+        c_used = ctypes.c_int(0)
+        rc = msm.shim_verify_sums(b"".join(cms), b"".join(prs), zy, r.to_bytes(32, "big"), ctypes.c_uint64(first), n, force_c, a, b,
+                                  ctypes.byref(c_used))
+        assert rc == 0
+        assert bytes(a) == bytes(b), (n, force_c, c_used.value, r, first)
+        s = sum(pow(r, first + i, R) * ys[i] for i in range(n)) % R
+        assert int.from_bytes(bytes(a)[96:128], "little") == s
+        if force_c:
+            assert c_used.value == force_c
