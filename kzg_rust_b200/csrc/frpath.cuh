@@ -132,13 +132,16 @@ __global__ void __launch_bounds__(64) k_challenge(const uint8_t *__restrict__ bl
     st_fr(z_out + b, z);
 }
 
-// The same hash with one WARP per blob, for small batches.  A hash stream is sequential, and a warp running 32 streams
-// (or one) spends 2 cycles per instruction on ~1500 instructions per compression: 3.1 ms per blob whatever the batch.
-// A third of those instructions are the message schedule, which does not depend on the running state: here lane l
-// expands the schedule of block 32 g + l (W_t + K_t for the 64 rounds, through shared memory), and the warp then runs
-// only the 64 rounds of each of the 32 blocks in turn: 2.2 ms per blob.  Used up to KZG_CHALLENGE_WARP_MAX blobs (about one
-// warp per scheduler); above that the one-thread-per-blob kernel has the better throughput.
-#define KZG_CHALLENGE_WARP_MAX 512
+// The same hash with G LANES per blob (G = 32, 16, 8, 4, 2), for batches that cannot fill the GPU with one stream per
+// thread.  A hash stream is sequential, and a warp -- whether it carries 32 streams or one -- issues one instruction
+// every 2 cycles (the 16-lane integer pipe of its scheduler): ~1000 instructions per compression for the 64 rounds and
+// ~600 for the message schedule, 3.1 - 4 ms per blob for any batch up to one warp per scheduler (592 warps = 18,944
+// streams).  The schedule does not depend on the running state: here the G lanes of a blob expand the schedules of G
+// consecutive blocks at once (W_t + K_t for the 64 rounds, through shared memory), then every lane runs only the rounds
+// of those G blocks in turn (the G lanes of a blob redundantly): 1024 + 600 / G instructions per compression, i.e.
+// 1.9 ms per blob at G = 32 (one warp per blob, up to 592 blobs) ... 2.4 ms at G = 4 (8 blobs per warp, up to 4,736).
+// fr_launch_challenge picks the largest G that keeps the launch at one warp per scheduler.
+#define KZG_CHALLENGE_GROUP_WARPS 592
 // big-endian message word j of the 64-byte block blk of  "FSBLOBVERIFY_V1_" || u64be(0) || u64be(n) || blob || commitment || padding
 KZG_D uint32_t challenge_msg_word(const uint8_t *__restrict__ blob, const uint8_t *__restrict__ cm, int n, uint32_t blk, int j) {
     const uint32_t m = 64u * blk + 4u * (uint32_t)j, blob_end = 32u + 32u * (uint32_t)n, msg_end = blob_end + 48u;
@@ -153,13 +156,17 @@ KZG_D uint32_t challenge_msg_word(const uint8_t *__restrict__ blob, const uint8_
     if (blk == nblocks - 1 && j == 15) return msg_end * 8u;  // the bit length fits 32 bits
     return 0u;
 }
-__global__ void __launch_bounds__(128) k_challenge_warp(const uint8_t *__restrict__ blobs, const uint8_t *__restrict__ commitments,
-                                                        uint32_t count, int n, fr_t *__restrict__ z_out) {
-    __shared__ uint32_t kw[4][64 * 32];  // [round t][block in the group]: conflict-free writes, broadcast reads
+template <int G>
+__global__ void __launch_bounds__(128) k_challenge_group(const uint8_t *__restrict__ blobs, const uint8_t *__restrict__ commitments,
+                                                         uint32_t count, int n, fr_t *__restrict__ z_out) {
+    __shared__ uint32_t kw[4][64 * 32];  // [round t][lane]: conflict-free writes; reads are broadcasts inside a blob's lanes
     constexpr uint32_t K[64] = {KZG_SHA256_K};
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t b = blockIdx.x * 4 + warp;
-    if (b >= count) return;  // the whole warp
+    constexpr uint32_t PER_WARP = 32 / G;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, slot = lane / G, sub = lane % G;
+    if ((blockIdx.x * 4 + warp) * PER_WARP >= count) return;  // the whole warp
+    // a warp's last slots may be past the end: they hash the last blob again and write nothing
+    const uint32_t b = min((blockIdx.x * 4 + warp) * PER_WARP + slot, count - 1);
+    const bool live = (blockIdx.x * 4 + warp) * PER_WARP + slot < count;
     const uint8_t *blob = blobs + (size_t)b * n * 32;
     const uint8_t *cm = commitments + (size_t)b * 48;
     const uint32_t msg_end = 32u + 32u * (uint32_t)n + 48u, nblocks = (msg_end + 9u + 63u) / 64u;
@@ -167,8 +174,8 @@ __global__ void __launch_bounds__(128) k_challenge_warp(const uint8_t *__restric
     sha256_init(h);
     uint32_t *mine = kw[warp];
 #pragma unroll 1
-    for (uint32_t base = 0; base < nblocks; base += 32) {
-        const uint32_t blk = base + lane;
+    for (uint32_t base = 0; base < nblocks; base += G) {
+        const uint32_t blk = base + sub;
         if (blk < nblocks) {
             uint32_t w[16];
             if (blk >= 1 && 64u * blk + 64u <= 32u + 32u * (uint32_t)n) {  // both halves inside the blob: 128-bit loads
@@ -194,16 +201,17 @@ __global__ void __launch_bounds__(128) k_challenge_warp(const uint8_t *__restric
             }
         }
         __syncwarp();
-        const uint32_t nb = min(32u, nblocks - base);
+        const uint32_t nb = min((uint32_t)G, nblocks - base);
 #pragma unroll 1
         for (uint32_t i = 0; i < nb; i++) {
+            const uint32_t col = slot * G + i;
             uint32_t a = h[0], bb = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
 #pragma unroll
             for (int t = 0; t < 64; t++) {
-                // One warp runs one dependent chain, so the depth of a round is what counts: h + K + W and d + h + K + W
-                // do not depend on this round's e, which leaves rotate -> xor -> ONE three-input add on the path from
-                // e to the next e (and from a to the next a), where the textbook order has three adds.
-                const uint32_t hkw = hh + mine[t * 32 + i], dhkw = d + hkw;
+                // A scheduler that carries one warp runs one dependent chain, so the depth of a round counts too:
+                // h + K + W and d + h + K + W do not depend on this round's e, which leaves rotate -> xor -> ONE
+                // three-input add on the path from e to the next e (and from a to the next a).
+                const uint32_t hkw = hh + mine[t * 32 + col], dhkw = d + hkw;
                 const uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
                 const uint32_t ch = (e & f) ^ (~e & g);
                 const uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(128) k_challenge_warp(const uint8_t *__restric
         }
         __syncwarp();
     }
-    if (lane == 0) {
+    if (sub == 0 && live) {
         fr_t z;
 #pragma unroll
         for (int i = 0; i < 8; i++) z.l[i] = h[7 - i];

@@ -19,7 +19,7 @@ __global__ void k_decode_g1(const uint8_t *in, g1_affine_t *out, int32_t *status
 int g1_launch_decode(cudaStream_t st, const uint8_t *d_in, g1_affine_t *d_out, int32_t *d_status, size_t count, int check_subgroup,
                      size_t status_mod) {
     if (count == 0) return KZG_B200_OK;
-    k_decode_g1<<<blocks_for(count, 64), 64, 0, st>>>(d_in, d_out, d_status, (uint32_t)count, check_subgroup, (uint32_t)status_mod);
+    k_decode_g1<<<blocks_for(count, 128), 128, 0, st>>>(d_in, d_out, d_status, (uint32_t)count, check_subgroup, (uint32_t)status_mod);
     CU(cudaGetLastError());
     return KZG_B200_OK;
 }
@@ -38,7 +38,7 @@ __global__ void k_decode_g1_pair(const uint8_t *in_a, const uint8_t *in_b, g1_af
 int g1_launch_decode2(cudaStream_t st, const uint8_t *d_commitments, const uint8_t *d_proofs, g1_affine_t *d_cpts, g1_affine_t *d_ppts,
                       int32_t *d_status, size_t count, int check_subgroup) {
     if (count == 0) return KZG_B200_OK;
-    k_decode_g1_pair<<<blocks_for(2 * count, 64), 64, 0, st>>>(d_commitments, d_proofs, d_cpts, d_ppts, d_status, (uint32_t)count, check_subgroup);
+    k_decode_g1_pair<<<blocks_for(2 * count, 128), 128, 0, st>>>(d_commitments, d_proofs, d_cpts, d_ppts, d_status, (uint32_t)count, check_subgroup);
     CU(cudaGetLastError());
     return KZG_B200_OK;
 }

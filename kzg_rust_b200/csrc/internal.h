@@ -109,6 +109,7 @@ struct kzg_b200_ctx {
     size_t va_n = 0;
     uint8_t va_digest[32];
     cudaStream_t stream = nullptr;
+    size_t call_blobs = 0;            // blobs of the call being enqueued (set by the entry points, under `mu`)
     uint64_t launches = 0;
     // optional per-stage device timing (CUDA events on `stream`), see kzg_b200_profile_*
     bool profile = false;
@@ -156,7 +157,9 @@ int g1_launch_tau_identity(cudaStream_t st, const uint8_t *d_commitments, const 
 
 // ---- frops.cu
 int fr_setup_roots_device(int n, kzg::fr_t **d_roots, cudaStream_t stream);
-int fr_launch_challenge(cudaStream_t st, const uint8_t *d_blobs, const uint8_t *d_commitments, size_t count, int n, kzg::fr_t *d_z);
+// call_blobs: blobs of the whole call this launch is a chunk of (picks the form of the hash kernel)
+int fr_launch_challenge(cudaStream_t st, const uint8_t *d_blobs, const uint8_t *d_commitments, size_t count, int n, kzg::fr_t *d_z,
+                        size_t call_blobs, int sms);
 int fr_launch_load_scalars(cudaStream_t st, const uint8_t *d_in, size_t count, kzg::fr_t *d_out, int32_t *d_status);
 // y_i = p_i(z_i) (+ the quotient (p_i(X) - y_i)/(X - z_i) as canonical scalars in d_inv when quotient != 0)
 int fr_launch_eval(cudaStream_t st, int quotient, const uint8_t *d_blobs, const kzg::fr_t *d_z, const kzg::fr_t *d_roots, int n,

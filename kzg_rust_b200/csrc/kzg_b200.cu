@@ -402,6 +402,7 @@ template <class Upload, class Run, class Finish>
 static int staged_chunks(kzg_b200_ctx *ctx, size_t n, Upload upload, Run run, Finish finish) {
     const size_t nchunks = (n + ctx->chunk - 1) / ctx->chunk;
     const size_t ahead = KZG_SLOTS - 1;
+    ctx->call_blobs = n;
     auto enqueue_upload = [&](size_t i) -> int {
         int slot = (int)(i % KZG_SLOTS);
         size_t off = i * ctx->chunk, cnt = std::min(ctx->chunk, n - off);

@@ -46,7 +46,7 @@ static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t 
         if (side) RC(decode_points_side(ctx, d_commitments, ln->d_pts, d_status, count, 1, count));
         else RC(decode_points(ctx, d_commitments, ln->d_pts, d_status, count, 1, count));
         stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
-        int rc = fr_launch_challenge(st, d_blobs, d_commitments, count, ctx->n, ln->d_z);
+        int rc = fr_launch_challenge(st, d_blobs, d_commitments, count, ctx->n, ln->d_z, ctx->call_blobs, ctx->sms);
         stage_end(ctx, 1);
         RC(rc);
     } else {
@@ -88,12 +88,13 @@ extern "C" int kzg_b200_compute_blob_kzg_proof_device(kzg_b200_ctx *ctx, const u
         CU(cudaMemsetAsync(d_status, 0, n * sizeof(int32_t), ctx->stream));
         RC(decode_points(ctx, d_commitments, reinterpret_cast<g1_affine_t *>(ctx->d_z_all + n), d_status, n, 1, n));
         stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
-        int rc = fr_launch_challenge(ctx->stream, d_blobs, d_commitments, n, ctx->n, ctx->d_z_all);
+        int rc = fr_launch_challenge(ctx->stream, d_blobs, d_commitments, n, ctx->n, ctx->d_z_all, n, ctx->sms);
         stage_end(ctx, 1);
         ctx->launches++;
         RC(rc);
         d_z_all = ctx->d_z_all;
     }
+    ctx->call_blobs = n;
     DeferredCompress dc;
     RC(deferred_begin(ctx, n, &dc));
     RC(lanes_begin(ctx));
@@ -229,7 +230,7 @@ static int verify_chunk_a(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8
     RC(rc);
     if (side) CU(cudaEventRecord(ln->ev_side_join, sd));
     stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
-    rc = fr_launch_challenge(sm, d_blobs, d_commitments, cnt, ctx->n, ln->d_z);
+    rc = fr_launch_challenge(sm, d_blobs, d_commitments, cnt, ctx->n, ln->d_z, ctx->call_blobs, ctx->sms);
     stage_end(ctx, 1);
     RC(rc);
     stage_begin(ctx, KZG_B200_STAGE_EVAL);
@@ -461,7 +462,7 @@ extern "C" int kzg_b200_verify_blob_kzg_proof_batch_device(kzg_b200_ctx *ctx, co
     RC(rc);
     CU(cudaEventRecord(ln->ev_side_join, sd));
     stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
-    rc = fr_launch_challenge(sm, d_blobs, d_commitments, n, ctx->n, ctx->d_z_all);
+    rc = fr_launch_challenge(sm, d_blobs, d_commitments, n, ctx->n, ctx->d_z_all, n, ctx->sms);
     stage_end(ctx, 1);
     RC(rc);
     ctx->launches += 2;

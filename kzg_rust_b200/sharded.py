@@ -85,7 +85,7 @@ def _all_gather_bytes(local, sizes, device):
     return [o.cpu().numpy()[:sz] for o, sz in zip(outs, sizes)] if sizes else []
 
 
-def verify_blob_kzg_proof_batch_sharded(backend, blobs, commitments, proofs, n_total, device="cpu"):
+def verify_blob_kzg_proof_batch_sharded(backend, blobs, commitments, proofs, n_total, device="cpu", trace=None):
     """Every rank passes ITS contiguous shard (shard_range(n_total, rank, world)) and gets the
     verdict for the whole batch.  Raises BadArgs on every rank if any shard holds a malformed blob,
     commitment or proof (the reference's first-error abort, src/kzg.rs:671-683, seen from outside).
@@ -93,9 +93,17 @@ def verify_blob_kzg_proof_batch_sharded(backend, blobs, commitments, proofs, n_t
     Two collectives per verdict: one all_gather of the shards' records (status byte + 160 B per blob: C_i, z_i,
     y_i, proof_i -- exactly what compute_r_powers hashes, so every rank derives the same r without a broadcast),
     and one all_gather of the 224-byte partial sums (+ status byte)."""
+    import time
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
+    t_last = [time.perf_counter()]
+
+    def mark(name):  # trace: a dict that receives the wall-clock milliseconds of every step on this rank
+        if trace is not None:
+            now = time.perf_counter()
+            trace[name] = trace.get(name, 0.0) + (now - t_last[0]) * 1e3
+            t_last[0] = now
     lo, hi = shard_range(n_total, rank, world)
     n_local = hi - lo
     blobs, commitments, proofs = _u8(blobs), _u8(commitments), _u8(proofs)
@@ -104,6 +112,7 @@ def verify_blob_kzg_proof_batch_sharded(backend, blobs, commitments, proofs, n_t
     if n_total == 0:
         return True
     rc, zy = backend.phase_a(blobs, commitments, proofs) if n_local else (0, np.zeros(0, np.uint8))
+    mark("phase_a")
     if world > 1:
         counts = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
         rec = np.zeros(1 + 160 * n_local, dtype=np.uint8)
@@ -125,8 +134,11 @@ def verify_blob_kzg_proof_batch_sharded(backend, blobs, commitments, proofs, n_t
         if rc:
             _k._raise(rc, "verify_blob_kzg_proof_batch (phase A)")
         all_c, all_p, all_zy = commitments, proofs, zy
+    mark("exchange_records")
     r = backend.compute_r(all_c, all_zy, all_p)       # every rank hashes the same bytes: no broadcast needed
+    mark("compute_r")
     rc, part = backend.phase_b(commitments, zy, proofs, r, lo)
+    mark("phase_b")
     if world > 1:
         rec = np.concatenate([np.array([min(rc, 255)], dtype=np.uint8), part])
         recs = _all_gather_bytes(rec, [225] * world, device)
@@ -134,6 +146,9 @@ def verify_blob_kzg_proof_batch_sharded(backend, blobs, commitments, proofs, n_t
         parts = np.concatenate([x[1:] for x in recs])
     else:
         parts = part
+    mark("exchange_partials")
     if rc:
         _k._raise(rc, "verify_blob_kzg_proof_batch (phase B)")
-    return backend.finish(parts)
+    ok = backend.finish(parts)
+    mark("finish")
+    return ok

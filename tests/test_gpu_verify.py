@@ -124,16 +124,23 @@ def test_two_phase_sharded_verify_matches_single_call():
         assert k.Kzg.verify_blob_kzg_proof_batch_raw(blobs, cms, pr, n, s) is (not tamper)
 
 
-def test_challenge_and_evaluation_match_oracle():
-    """z_i and y_i of phase A are bit-exact with compute_challenge /
-    evaluate_polynomial_in_evaluation_form of the oracle."""
+@pytest.mark.parametrize("lanes_per_blob", [0, 32, 16, 8, 4, 2, 1])
+def test_challenge_and_evaluation_match_oracle(lanes_per_blob):
+    """z_i and y_i of phase A are bit-exact with compute_challenge / evaluate_polynomial_in_evaluation_form of the
+    oracle, for every form of the hash kernel (G lanes per blob, csrc/frpath.cuh; 0 = the size rule, 1 = one thread
+    per blob) and a batch that does not fill its last warp."""
     k = _kzg()
     L = k.load_library()
     s = gpu_settings("mainnet", 8)
     o = oracle_settings("mainnet")
     blobs, cms, proofs = _make_batch(k, s, 5, 5)
     zy = np.zeros((5, 64), dtype=np.uint8)
-    assert L.kzg_b200_verify_phase_a(s._h, blobs.ctypes.data, cms.ctypes.data, proofs.ctypes.data, 5, zy.ctypes.data) == 0
+    if lanes_per_blob:
+        os.environ["KZG_B200_CHALLENGE_G"] = str(lanes_per_blob)
+    try:
+        assert L.kzg_b200_verify_phase_a(s._h, blobs.ctypes.data, cms.ctypes.data, proofs.ctypes.data, 5, zy.ctypes.data) == 0
+    finally:
+        os.environ.pop("KZG_B200_CHALLENGE_G", None)
     for i in range(5):
         z = o.compute_challenge(blobs[i].tobytes(), cms[i].tobytes())
         assert zy[i, :32].tobytes() == z
