@@ -153,7 +153,7 @@ KZG_HD void hy_product(uint32_t *T, const fp_t &a, const fp_t &b) {
 // Same even/odd 64-bit-column scheme as fe_mul (bigint.cuh) without the operand rows:
 // U = (T_lo + M mod) / R is built in N steps of one IMAD (m), N wide multiply-adds (m * mod) and
 // a shift; the result is U + T_hi, reduced once.
-template <class P> KZG_HD void fe_redc(Fe<P> &r, const uint32_t *T) {
+template <class P, bool REDUCE = true> KZG_HD void fe_redc(Fe<P> &r, const uint32_t *T) {
     constexpr int N = P::N;
     uint32_t mp[N];
 #pragma unroll
@@ -195,7 +195,7 @@ template <class P> KZG_HD void fe_redc(Fe<P> &r, const uint32_t *T) {
 #pragma unroll
     for (int k = 1; k < N; k++) t.l[k] = addc_cc(t.l[k], T[N + k], cc);
     uint32_t top = addc(0, 0, cc);
-    fe_reduce_once(t, top);
+    if (REDUCE) fe_reduce_once(t, top);  // lazy form: T < 4 mod^2 gives (T + M mod) / R < 2 mod < 2^(32N), no carry out
     r = t;
 }
 
@@ -208,6 +208,12 @@ KZG_HD void fp_sqr_hybrid(fp_t &r, const fp_t &a) {
     uint32_t T[24];
     hy_product<true>(T, a, a);
     fe_redc(r, T);
+}
+// a in [0, 2p) -> a^2 / R in [0, 2p)
+KZG_HD void fp_sqr_hybrid_lazy(fp_t &r, const fp_t &a) {
+    uint32_t T[24];
+    hy_product<true>(T, a, a);
+    fe_redc<FpParams, false>(r, T);
 }
 
 }  // namespace kzg

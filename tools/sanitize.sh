@@ -15,3 +15,7 @@ run memcheck tests/test_gpu_proof.py "compute_blob_kzg_proof_vectors and g8"
 run memcheck tests/test_gpu_verify.py "verify_blob_kzg_proof_batch_vectors and g8"
 run racecheck tests/test_gpu_commit.py "reference_vectors and g8"
 run racecheck tests/test_gpu_proof.py "compute_blob_kzg_proof_vectors and g8"
+# the bucket method of phase B (shared-memory tree of k_pip_rows, the counting sort) and the grouped challenge hash
+run memcheck tests/test_gpu_verify.py "bucket_method and (6 or 64 or 300)"
+run racecheck tests/test_gpu_verify.py "verify_blob_kzg_proof_batch_vectors and g8"
+run racecheck tests/test_gpu_verify.py "challenge_and_evaluation"
