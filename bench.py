@@ -420,13 +420,10 @@ def main():
     blobs_timed = B  # the profiled step
     achieved = IMAD_PER_COMMIT * blobs_timed / (msm_ms * 1e-3) if msm_ms > 0 else 0.0
     groups = -(-4096 // comb_width)
-    # what this design executes per blob: 255 bit positions x (groups - 1) affine additions x (5 products + 1 squaring), plus
-    # the Horner pass (254 doublings at 7 products + 254 mixed additions at 11); 600 IMAD issue slots per all-integer product
-    # (300 wide multiply-adds); the squaring of an addition is two-pipe (csrc/fp_twopipe.cuh): 156 wide multiply-adds = 312
-    # IMAD issue slots on the integer pipe and 36 partial products (144 instructions) on the FP64 pipe
+    # what this design executes per blob: 255 bit positions x (groups - 1) affine additions x 6 products, plus the
+    # Horner pass (254 doublings at 7 products + 254 mixed additions at 11); 600 IMAD issue slots per product
     additions = 255 * (groups - 1)
-    executed_imad = additions * (5 * 600.0 + 312.0) + 254 * 18 * 600.0
-    executed_fp64 = additions * 144.0
+    executed_imad = (additions * 6 + 254 * 18) * 600.0
     traffic, traffic_src = ncu_traffic(comb_width)
     roofline = {
         "bound": "imad", "kernel": "batch_add_kernel (GatherPolicy + PairPolicy launches)",
@@ -439,9 +436,7 @@ def main():
         "wide_mac_per_s": imadw.value, "fp_mul_per_s": fpmul.value,
         "whole_step_frac": IMAD_PER_COMMIT * value / world / imad.value if imad.value else None,
         # against the work this design actually executes
-        "additions_per_blob": additions, "executed_imad_per_blob": executed_imad, "executed_fp64_instr_per_blob": executed_fp64,
-        # field products per second of the MSM kernels against the rate of dependent all-integer products measured in this process
-        "products_frac": additions * 6 * blobs_timed / (msm_ms * 1e-3) / fpmul.value if fpmul.value and msm_ms > 0 else None,
+        "additions_per_blob": additions, "executed_imad_per_blob": executed_imad,
         "executed_frac": executed_imad * blobs_timed / (msm_ms * 1e-3) / imad.value if imad.value and msm_ms > 0 else None,
         "executed_whole_step_frac": executed_imad * value / world / imad.value if imad.value else None,
         "additions_per_s": additions * blobs_timed / (msm_ms * 1e-3) if msm_ms > 0 else None,

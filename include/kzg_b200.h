@@ -198,7 +198,7 @@ int kzg_b200_measure_peaks(kzg_b200_ctx *ctx, double *imad_per_s, double *imad_w
 
 /* Test aids (tests/test_gpu_field.py, tests/test_gpu_commit.py): device field arithmetic on arrays of raw
  * limbs -- op 0: Fp mul, 1: Fp inverse, 2: Fr mul (8 words per element, all others 12), 3: Fp add, 4: Fp sub,
- * 7 / 8 / 9: Fp mul / sub / two-pipe squaring on lazy residues in [0, 2p) (what the MSM levels use) -- and a read-back of precomputed
+ * 7 / 8: Fp mul / sub on lazy residues in [0, 2p) (what the MSM levels use) -- and a read-back of precomputed
  * table entries (flat index: group q, entry idx -> q * 2^(g-1) + idx; 96 B each, affine Montgomery limbs). */
 int kzg_b200_debug_field_op(kzg_b200_ctx *ctx, int op, const uint32_t *a, const uint32_t *b, uint32_t *out, uint64_t count);
 int kzg_b200_debug_table(kzg_b200_ctx *ctx, uint64_t first, uint64_t count, void *out);

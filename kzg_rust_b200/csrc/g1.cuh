@@ -4,7 +4,9 @@
 // (reference src/utils.rs:221-227, 282-315).
 #pragma once
 #include "fields.cuh"
-#include "fp_twopipe.cuh"
+#if defined(KZG_SQR_HYBRID)
+#include "../../tools/experiments/fp_hybrid.cuh"
+#endif
 
 namespace kzg {
 
@@ -74,12 +76,10 @@ KZG_HD void add_finish(g1_affine_t &r, int kind, const g1_affine_t &p1, const g1
         else fe_sub(num, p2.y, p1.y);
     }
     fpx_mul<LAZY>(lam, num, inv);
-    // the squaring goes to the FP64 pipe + half the integer multiply-adds (fp_twopipe.cuh); KZG_SQR_INTEGER builds the
-    // all-integer form for A/B runs
-#if defined(KZG_SQR_INTEGER)
-    fpx_mul<LAZY>(t, lam, lam);
+#if defined(KZG_SQR_HYBRID) && defined(__CUDA_ARCH__)
+    if (LAZY) fp_sqr_hybrid_lazy(t, lam); else fe_mul(t, lam, lam);
 #else
-    if (LAZY) fp_sqr_twopipe_lazy(t, lam); else fe_sqr(t, lam);
+    fpx_mul<LAZY>(t, lam, lam);
 #endif
     fpx_sub<LAZY>(t, t, p1.x);
     fpx_sub<LAZY>(t, t, p2.x);  // x3 (p2.x == p1.x mod p when doubling)

@@ -264,7 +264,7 @@ int g1_measure_peaks(kzg_b200_ctx *ctx, double *imad_per_s, double *imad_wide_pe
 
 // ------------------------------------------------------------------ device field operations on arrays (unit tests)
 // op 0: Fp mul, 1: Fp inverse (b ignored), 2: Fr mul (8 words per element, all others 12), 3: Fp add, 4: Fp sub,
-// 7: lazy Fp mul, 8: lazy Fp sub, 9: lazy two-pipe Fp squaring (b ignored) -- operands and results in [0, 2p).
+// 7: lazy Fp mul, 8: lazy Fp sub -- operands and results in [0, 2p).
 __global__ void k_debug_field_op(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, uint64_t count) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -282,12 +282,11 @@ __global__ void k_debug_field_op(int op, const uint32_t *a, const uint32_t *b, u
     else if (op == 3) fe_add(z, x, y);
     else if (op == 7) fe_mul_lazy(z, x, y);
     else if (op == 8) fe_sub_lazy(z, x, y);
-    else if (op == 9) fp_sqr_twopipe_lazy(z, x);
     else fe_sub(z, x, y);
     for (int k = 0; k < 12; k++) out[12 * i + k] = z.l[k];
 }
 int g1_debug_field_op(kzg_b200_ctx *ctx, int op, const uint32_t *a, const uint32_t *b, uint32_t *out, uint64_t count) {
-    if (!(op >= 0 && op <= 4) && !(op >= 7 && op <= 9)) return KZG_B200_BAD_ARGS;
+    if (!(op >= 0 && op <= 4) && op != 7 && op != 8) return KZG_B200_BAD_ARGS;
     const size_t w = op == 2 ? 8 : 12;
     DeviceBuf d;
     CU(d.alloc(3 * count * w * 4));

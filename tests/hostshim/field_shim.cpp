@@ -1,7 +1,7 @@
 // Host-side shim exposing the product's field templates (host code path of
 // kzg_rust_b200/csrc/bigint.cuh) to ctypes, so tests can compare them with Python ints.
 #include "../../kzg_rust_b200/csrc/fields.cuh"
-#include "../../kzg_rust_b200/csrc/fp_twopipe.cuh"
+#include "../../tools/experiments/fp_hybrid.cuh"
 using namespace kzg;
 extern "C" {
 void shim_fp_mul2(const uint32_t *a1, const uint32_t *b1, const uint32_t *a2, const uint32_t *b2, uint32_t *r1, uint32_t *r2) {
@@ -31,13 +31,13 @@ void shim_fr_mul_many(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t 
     for (size_t i = 0; i < count; i++) shim_fr_mul(a + 8 * i, b + 8 * i, r + 8 * i);
 }
 }
-// the two-pipe (FP64 product + IMAD reduction) multiplication of fp_twopipe.cuh, host code path
+// the two-pipe (FP64 product + IMAD reduction) multiplication of fp_hybrid.cuh, host code path
 extern "C" {
 void shim_fp_mul_hybrid_many(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t count) {
     for (size_t i = 0; i < count; i++) {
         fp_t x, y, z;
         memcpy(x.l, a + 12 * i, 48); memcpy(y.l, b + 12 * i, 48);
-        fp_mul_twopipe(z, x, y);
+        fp_mul_hybrid(z, x, y);
         memcpy(r + 12 * i, z.l, 48);
     }
 }
@@ -45,7 +45,7 @@ void shim_fp_sqr_hybrid_many(const uint32_t *a, uint32_t *r, size_t count) {
     for (size_t i = 0; i < count; i++) {
         fp_t x, z;
         memcpy(x.l, a + 12 * i, 48);
-        fp_sqr_twopipe(z, x);
+        fp_sqr_hybrid(z, x);
         memcpy(r + 12 * i, z.l, 48);
     }
 }
@@ -76,14 +76,4 @@ void shim_fp_sub_lazy4_many(const uint32_t *a, const uint32_t *b, uint32_t *r, s
     for (size_t i = 0; i < count; i++) { fp_t x, y, z; memcpy(x.l, a + 12 * i, 48); memcpy(y.l, b + 12 * i, 48); fe_sub_lazy4(z, x, y); memcpy(r + 12 * i, z.l, 48); }
 }
 int shim_fp_is_zero_lazy4(const uint32_t *a) { fp_t x; memcpy(x.l, a, 48); return fe_is_zero_lazy4(x); }
-}
-
-// the lazy squaring of the MSM levels: a in [0, 2p) -> a^2 / R in [0, 2p)
-extern "C" void shim_fp_sqr_twopipe_lazy_many(const uint32_t *a, uint32_t *r, size_t count) {
-    for (size_t i = 0; i < count; i++) {
-        fp_t x, z;
-        memcpy(x.l, a + 12 * i, 48);
-        fp_sqr_twopipe_lazy(z, x);
-        memcpy(r + 12 * i, z.l, 48);
-    }
 }

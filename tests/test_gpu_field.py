@@ -71,13 +71,3 @@ def test_lazy_fp_ops_stay_below_2p():
     got = _run(8, av, bv, 12)
     assert all(g < 2 * P for g in got)
     assert [g % P for g in got] == [(x - y) % P for x, y in zip(av, bv)]
-
-
-def test_two_pipe_squaring_on_the_device():
-    """fp_sqr_twopipe_lazy (FP64-pipe partial products + integer Montgomery reduction, csrc/fp_twopipe.cuh), the squaring
-    inside every addition of the MSM levels: results below 2p and congruent to x^2 / R for canonical and lazy operands."""
-    Rp_inv = pow(pow(2, 384, P), -1, P)
-    av, _ = _values(P, 2 * P, 20000, 5)
-    got = _run(9, av, av, 12)
-    assert all(g < 2 * P for g in got)
-    assert [g % P for g in got] == [x * x * Rp_inv % P for x in av]

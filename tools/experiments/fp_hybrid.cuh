@@ -1,4 +1,4 @@
-// fp_twopipe.cuh -- Fp squaring (and, for the micro-benchmarks, multiplication) split over TWO multiplier pipes of the B200 SM.
+// fp_hybrid.cuh -- Fp multiplication split over TWO multiplier pipes of the B200 SM.
 //
 // The IMAD pipe (16 lanes per SM sub-partition, one 32x32+64 multiply-add per 4 clocks per
 // warp) is the roofline of the all-integer fe_mul (bigint.cuh): 288 wide multiply-adds per
@@ -19,18 +19,10 @@
 // the multiplier work is spread over two pipes and the result is bit-identical to fe_mul
 // (canonical residue < p).  Squaring needs 36 partial products instead of 64.
 //
-// Where it is used: the one squaring of every affine addition of the MSM levels (lambda^2, g1.cuh add_finish) is
-// fp_sqr_twopipe_lazy -- 36 partial products on the FP64 pipe + 156 wide multiply-adds, against 300 for fe_mul_lazy.
-// Measured (tools/ubench.cu): dependent squarings 3.6e10/s against 3.0e10/s for the all-integer product at twelve warps per
-// SM; in the MSM (profiles/sweep_r2x.log) the levels get 3 % shorter and the commitments/s 1.6 - 2 % higher (the FP64 pipe
-// costs power: the SM clock under the board's power cap goes from 1965 to 1942 MHz).  The general two-pipe product
-// (64 partial products) is NOT faster than fe_mul -- its ~200 conversion instructions eat the gain -- and is
-// instantiated only by tools/ubench.cu and the unit tests.
-//
 // Host build: the same code with fma() under FE_TOWARDZERO (tests/hostshim), so the limb
 // algebra is checked against Python integers on a CPU.
 #pragma once
-#include "fields.cuh"
+#include "../../kzg_rust_b200/csrc/fields.cuh"
 
 #if !defined(__CUDA_ARCH__)
 #include <cfenv>
@@ -207,18 +199,18 @@ template <class P, bool REDUCE = true> KZG_HD void fe_redc(Fe<P> &r, const uint3
     r = t;
 }
 
-KZG_HD void fp_mul_twopipe(fp_t &r, const fp_t &a, const fp_t &b) {
+KZG_HD void fp_mul_hybrid(fp_t &r, const fp_t &a, const fp_t &b) {
     uint32_t T[24];
     hy_product<false>(T, a, b);
     fe_redc(r, T);
 }
-KZG_HD void fp_sqr_twopipe(fp_t &r, const fp_t &a) {
+KZG_HD void fp_sqr_hybrid(fp_t &r, const fp_t &a) {
     uint32_t T[24];
     hy_product<true>(T, a, a);
     fe_redc(r, T);
 }
 // a in [0, 2p) -> a^2 / R in [0, 2p)
-KZG_HD void fp_sqr_twopipe_lazy(fp_t &r, const fp_t &a) {
+KZG_HD void fp_sqr_hybrid_lazy(fp_t &r, const fp_t &a) {
     uint32_t T[24];
     hy_product<true>(T, a, a);
     fe_redc<FpParams, false>(r, T);

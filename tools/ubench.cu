@@ -9,7 +9,7 @@
 #include <cstdlib>
 
 #include "../kzg_rust_b200/csrc/fields.cuh"
-#include "../kzg_rust_b200/csrc/fp_twopipe.cuh"
+#include "experiments/fp_hybrid.cuh"
 
 using namespace kzg;
 
@@ -270,7 +270,7 @@ __global__ void k_halves_fp64(double *out, int iters) {
 
 // ---- fe_mul as a real call (code-size experiment: the addition kernel inlines 13 copies of it)
 __device__ __noinline__ fp_t fp_mul_call(fp_t a, fp_t b) { fp_t r; fe_mul(r, a, b); return r; }
-// ---- two-pipe multiplication (fp_twopipe.cuh): dependent chains, and a bit-for-bit check against fe_mul
+// ---- two-pipe multiplication (fp_hybrid.cuh): dependent chains, and a bit-for-bit check against fe_mul
 template <int MODE, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_fpmul_variant(fp_t *out, int iters) {
     fp_t x = fe_one<FpParams>(), y = fp_const_b();
@@ -279,9 +279,9 @@ __global__ void __launch_bounds__(128, MINB) k_fpmul_variant(fp_t *out, int iter
 #pragma unroll 1
     for (int i = 0; i < iters; i++) {
         if (MODE == 0) { fe_mul(x, x, y); fe_mul(y, y, x); }
-        if (MODE == 1) { fp_mul_twopipe(x, x, y); fp_mul_twopipe(y, y, x); }
-        if (MODE == 2) { fp_sqr_twopipe(x, x); fp_sqr_twopipe(y, y); }
-        if (MODE == 3) { fp_mul_twopipe(x, x, y); fe_mul(y, y, x); }
+        if (MODE == 1) { fp_mul_hybrid(x, x, y); fp_mul_hybrid(y, y, x); }
+        if (MODE == 2) { fp_sqr_hybrid(x, x); fp_sqr_hybrid(y, y); }
+        if (MODE == 3) { fp_mul_hybrid(x, x, y); fe_mul(y, y, x); }
         if (MODE == 4) { x = fp_mul_call(x, y); y = fp_mul_call(y, x); }
     }
     fe_add(x, x, y);
@@ -296,9 +296,9 @@ __global__ void k_hybrid_check(unsigned long long *bad, int iters) {
     for (int i = 0; i < iters; i++) {
         fp_t a, b, c, d;
         fe_mul(a, x, y);
-        fp_mul_twopipe(b, x, y);
+        fp_mul_hybrid(b, x, y);
         fe_mul(c, y, y);
-        fp_sqr_twopipe(d, y);
+        fp_sqr_hybrid(d, y);
         if (!fe_eq(a, b)) nbad++;
         if (!fe_eq(c, d)) nbad++;
         x = a;
