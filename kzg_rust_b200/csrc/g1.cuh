@@ -4,9 +4,6 @@
 // (reference src/utils.rs:221-227, 282-315).
 #pragma once
 #include "fields.cuh"
-#if defined(KZG_SQR_HYBRID)
-#include "../../tools/experiments/fp_hybrid.cuh"
-#endif
 
 namespace kzg {
 
@@ -76,11 +73,7 @@ KZG_HD void add_finish(g1_affine_t &r, int kind, const g1_affine_t &p1, const g1
         else fe_sub(num, p2.y, p1.y);
     }
     fpx_mul<LAZY>(lam, num, inv);
-#if defined(KZG_SQR_HYBRID) && defined(__CUDA_ARCH__)
-    if (LAZY) fp_sqr_hybrid_lazy(t, lam); else fe_mul(t, lam, lam);
-#else
     fpx_mul<LAZY>(t, lam, lam);
-#endif
     fpx_sub<LAZY>(t, t, p1.x);
     fpx_sub<LAZY>(t, t, p2.x);  // x3 (p2.x == p1.x mod p when doubling)
     fp_t u;
