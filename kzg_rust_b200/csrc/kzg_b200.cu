@@ -4,6 +4,7 @@
 // path runs on the GPU.  There is deliberately no CPU fallback: if CUDA is unusable the
 // entry points return KZG_B200_CUDA_ERROR.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <string>
 

@@ -421,12 +421,26 @@ extern "C" int kzg_b200_verify_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const uin
     // with r^0 = 1 does, so the same path serves both.
     std::vector<uint8_t> zy(n * 64);
     VerifyBufs vb;
+    // KZG_B200_TRACE=1: wall-clock milliseconds of the host-visible steps on stderr (tools/verify_stages.py)
+    const bool trace = env_int("KZG_B200_TRACE", 0) != 0;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[kzg_b200 trace] %-12s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     RC(verify_phase_a_locked(ctx, blobs, commitments, proofs, n, zy.data(), &vb));
+    lap("phase A");
     uint8_t r[32], partial[224];
     RC(kzg_b200_compute_r(ctx, commitments, zy.data(), proofs, n, r));
+    lap("compute_r");
     // phase A left the decoded points and the (z, y) records of the whole call on the device
     RC(verify_phase_b_device(ctx, vb, n, n, r, 0, partial));
-    return host_verify_finish(partial, 1, ctx->tau_prepared, ok) == 0 ? KZG_B200_OK : KZG_B200_BAD_ARGS;
+    lap("phase B");
+    int rc = host_verify_finish(partial, 1, ctx->tau_prepared, ok) == 0 ? KZG_B200_OK : KZG_B200_BAD_ARGS;
+    lap("finish");
+    return rc;
 }
 
 // The same for blobs, commitments and proofs that are already in this context's GPU memory (16-byte aligned).
