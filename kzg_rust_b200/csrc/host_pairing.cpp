@@ -495,10 +495,40 @@ static void miller_pair(Fp12 &f, const G2Prepared &q1, const G1 &p1, const G2Pre
         if ((BLS_X >> i) & 1) step(k++);
     }
 }
-static void fp12_pow_x(Fp12 &r, const Fp12 &a) {  // a^x for the (negative) curve parameter; a unitary
+// Squaring in the cyclotomic subgroup (where everything lives after the easy part of the final exponentiation):
+// Granger-Scott, "Faster squaring in the cyclotomic subgroup of sixth degree extensions" -- three squarings in
+// Fp4 = Fp2[y]/(y^2 - xi) instead of a full Fp12 squaring (18 base-field products instead of 36).
+static inline void fp4_sqr(Fp2 &r0, Fp2 &r1, const Fp2 &a, const Fp2 &b) {  // (a + b y)^2 = (a^2 + xi b^2) + 2ab y
+    Fp2 ab, s, t, xb;
+    fp2_mul(ab, a, b);
+    fp2_add(s, a, b);
+    fp2_mul_xi(xb, b); fp2_add(t, a, xb);
+    fp2_mul(s, s, t);
+    fp2_sub(s, s, ab);
+    fp2_mul_xi(t, ab); fp2_sub(r0, s, t);
+    fp2_dbl(r1, ab);
+}
+static void fp12_cyclotomic_sqr(Fp12 &r, const Fp12 &x) {
+    Fp2 z0 = x.a.c0, z4 = x.a.c1, z3 = x.a.c2, z2 = x.b.c0, z1 = x.b.c1, z5 = x.b.c2;
+    Fp2 t0, t1, t2, t3, t4, t5, tmp;
+    fp4_sqr(t0, t1, z0, z1);
+    fp4_sqr(t2, t3, z2, z3);
+    fp4_sqr(t4, t5, z4, z5);
+    auto three_minus_two = [](Fp2 &z, const Fp2 &t) { fp2_sub(z, t, z); fp2_dbl(z, z); fp2_add(z, z, t); };  // 3t - 2z
+    auto three_plus_two = [](Fp2 &z, const Fp2 &t) { fp2_add(z, t, z); fp2_dbl(z, z); fp2_add(z, z, t); };    // 3t + 2z
+    three_minus_two(z0, t0);
+    three_plus_two(z1, t1);
+    fp2_mul_xi(tmp, t5);
+    three_plus_two(z2, tmp);
+    three_minus_two(z3, t4);
+    three_minus_two(z4, t2);
+    three_plus_two(z5, t3);
+    r.a.c0 = z0; r.a.c1 = z4; r.a.c2 = z3; r.b.c0 = z2; r.b.c1 = z1; r.b.c2 = z5;
+}
+static void fp12_pow_x(Fp12 &r, const Fp12 &a) {  // a^x for the (negative) curve parameter; a in the cyclotomic subgroup
     Fp12 acc = a;
     for (int i = 62; i >= 0; i--) {
-        fp12_sqr(acc, acc);
+        fp12_cyclotomic_sqr(acc, acc);
         if ((BLS_X >> i) & 1) fp12_mul(acc, acc, a);
     }
     fp12_conj(r, acc);
