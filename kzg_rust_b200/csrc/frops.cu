@@ -15,21 +15,23 @@ static void launch_challenge_group(cudaStream_t st, const uint8_t *d_blobs, cons
     const size_t warps = (count * G + 31) / 32;
     k_challenge_group<G><<<blocks_for(warps, 4), 128, 0, st>>>(d_blobs, d_commitments, (uint32_t)count, n, d_z);
 }
+// The most lanes per blob that still leave every warp of the launch a scheduler of its own (frpath.cuh).  The validation of
+// the chunk's points (`beside` blocks of four warps, one thread per point) runs beside the hash and is just as latency-bound:
+// as long as both together have at most one block per SM, no scheduler carries two warps.  (Measured on whole calls,
+// tools/hash_form_ab.py: a hash block sharing an SM with a validation block runs 1.5 - 2x longer.)
+// A chunk of a larger call (call_blobs > count) runs beside the other lane's kernels, where instructions per blob count
+// and latency does not: one thread per blob.
+static int challenge_lanes_per_blob(size_t count, size_t call_blobs, size_t beside, int sms) {
+    const size_t budget = (size_t)sms > beside ? (size_t)sms - beside : 0;
+    int g = call_blobs > count ? 1 : 32;
+    while (g > 1 && (count * g + 127) / 128 > budget) g >>= 1;
+    return g;
+}
 int fr_launch_challenge(cudaStream_t st, const uint8_t *d_blobs, const uint8_t *d_commitments, size_t count, int n, fr_t *d_z,
                         size_t call_blobs, int sms) {
     if (count == 0) return KZG_B200_OK;
-    // The most lanes per blob that still leave every warp of the launch a scheduler of its own (frpath.cuh).  The validation of
-    // the chunk's 2 x count points runs beside the hash on the side stream, also latency-bound, also in blocks of four warps
-    // (g1ops.cu): as long as both launches together have at most one block per SM, no scheduler carries two warps.  (Measured
-    // on whole calls, tools/hash_form_ab.py: a hash block sharing an SM with a validation block runs 1.5 - 2x longer.)
-    // A chunk of a larger call (call_blobs > count) runs beside the other lane's kernels, where instructions per blob count
-    // and latency does not: one thread per blob.  KZG_B200_CHALLENGE_G forces a form.
-    int g = env_int("KZG_B200_CHALLENGE_G", 0);
-    if (g <= 0) {
-        const size_t beside = (2 * count + 127) / 128, budget = (size_t)sms > beside ? (size_t)sms - beside : 0;
-        g = call_blobs > count ? 1 : 32;
-        while (g > 1 && (count * g + 127) / 128 > budget) g >>= 1;
-    }
+    int g = env_int("KZG_B200_CHALLENGE_G", 0);  // forces a form
+    if (g <= 0) g = challenge_lanes_per_blob(count, call_blobs, (2 * count + 127) / 128, sms);
     switch (g) {
         case 32: launch_challenge_group<32>(st, d_blobs, d_commitments, count, n, d_z); break;
         case 16: launch_challenge_group<16>(st, d_blobs, d_commitments, count, n, d_z); break;

@@ -156,17 +156,17 @@ KZG_D uint32_t challenge_msg_word(const uint8_t *__restrict__ blob, const uint8_
     if (blk == nblocks - 1 && j == 15) return msg_end * 8u;  // the bit length fits 32 bits
     return 0u;
 }
+// one block of four warps; kw: 4 x 64 x 32 words of shared memory
 template <int G>
-__global__ void __launch_bounds__(128) k_challenge_group(const uint8_t *__restrict__ blobs, const uint8_t *__restrict__ commitments,
-                                                         uint32_t count, int n, fr_t *__restrict__ z_out) {
-    __shared__ uint32_t kw[4][64 * 32];  // [round t][lane]: conflict-free writes; reads are broadcasts inside a blob's lanes
+KZG_D void challenge_group_block(uint32_t (*kw)[64 * 32], uint32_t block, const uint8_t *__restrict__ blobs,
+                                 const uint8_t *__restrict__ commitments, uint32_t count, int n, fr_t *__restrict__ z_out) {
     constexpr uint32_t K[64] = {KZG_SHA256_K};
     constexpr uint32_t PER_WARP = 32 / G;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, slot = lane / G, sub = lane % G;
-    if ((blockIdx.x * 4 + warp) * PER_WARP >= count) return;  // the whole warp
+    if ((block * 4 + warp) * PER_WARP >= count) return;  // the whole warp
     // a warp's last slots may be past the end: they hash the last blob again and write nothing
-    const uint32_t b = min((blockIdx.x * 4 + warp) * PER_WARP + slot, count - 1);
-    const bool live = (blockIdx.x * 4 + warp) * PER_WARP + slot < count;
+    const uint32_t b = min((block * 4 + warp) * PER_WARP + slot, count - 1);
+    const bool live = (block * 4 + warp) * PER_WARP + slot < count;
     const uint8_t *blob = blobs + (size_t)b * n * 32;
     const uint8_t *cm = commitments + (size_t)b * 48;
     const uint32_t msg_end = 32u + 32u * (uint32_t)n + 48u, nblocks = (msg_end + 9u + 63u) / 64u;
@@ -231,7 +231,12 @@ __global__ void __launch_bounds__(128) k_challenge_group(const uint8_t *__restri
         st_fr(z_out + b, z);
     }
 }
-
+template <int G>
+__global__ void __launch_bounds__(128) k_challenge_group(const uint8_t *__restrict__ blobs, const uint8_t *__restrict__ commitments,
+                                                         uint32_t count, int n, fr_t *__restrict__ z_out) {
+    __shared__ uint32_t kw[4][64 * 32];  // [round t][lane]: conflict-free writes; reads are broadcasts inside a blob's lanes
+    challenge_group_block<G>(kw, blockIdx.x, blobs, commitments, count, n, z_out);
+}
 // caller-supplied evaluation points (compute_kzg_proof): 32 big-endian bytes each, must be
 // canonical (reference src/kzg.rs:452 -> bytes_to_bls_field)
 __global__ void k_load_scalars(const uint8_t *__restrict__ in, uint32_t count, fr_t *__restrict__ out, int32_t *status) {

@@ -96,6 +96,11 @@ struct kzg_b200_ctx {
     int32_t *d_status = nullptr;      // slots x chunk
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_h2d[KZG_SLOTS] = {nullptr, nullptr, nullptr}, ev_free[KZG_SLOTS] = {nullptr, nullptr, nullptr};
+    // a slot's commitments / proofs are uploaded BEFORE its blobs and get their own event: their validation starts while the
+    // blobs are still on their way (and so never starts at the same instant as the hash, see verify_chunk_a)
+    cudaEvent_t ev_aux[KZG_SLOTS] = {nullptr, nullptr, nullptr};
+    bool aux_recorded[KZG_SLOTS] = {false, false, false};
+    cudaEvent_t aux_ready = nullptr;  // ev_aux of the chunk being enqueued, when its upload recorded one
     host_g2_prepared *tau_prepared = nullptr;  // Miller-loop lines of [tau]G2
     kzg::g1_affine_t *d_sums_all = nullptr; // sums of a whole device-resident call, [bit position][blob] (grow-only)
     size_t sums_all_elems = 0;

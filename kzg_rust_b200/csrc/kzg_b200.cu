@@ -140,6 +140,7 @@ static int ctx_init(kzg_b200_ctx *ctx, const uint8_t *g1_lagrange, size_t n1, co
     for (int i = 0; i < KZG_SLOTS; i++) {
         CU(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_aux[i], cudaEventDisableTiming));
     }
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
@@ -264,6 +265,7 @@ extern "C" void kzg_b200_ctx_destroy(kzg_b200_ctx *ctx) {
     for (int i = 0; i < KZG_SLOTS; i++) {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
         if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
+        if (ctx->ev_aux[i]) cudaEventDestroy(ctx->ev_aux[i]);
     }
     stage_collect(ctx);
     host_g2_prepared_free(ctx->tau_prepared);
@@ -404,10 +406,19 @@ static int staged_chunks(kzg_b200_ctx *ctx, size_t n, Upload upload, Run run, Fi
     const size_t nchunks = (n + ctx->chunk - 1) / ctx->chunk;
     const size_t ahead = KZG_SLOTS - 1;
     ctx->call_blobs = n;
+    const bool trace = env_int("KZG_B200_TRACE", 0) == 3;  // host wall clock of the enqueue / wait phases on stderr
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[kzg_b200 trace]   staged: %-10s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     auto enqueue_upload = [&](size_t i) -> int {
         int slot = (int)(i % KZG_SLOTS);
         size_t off = i * ctx->chunk, cnt = std::min(ctx->chunk, n - off);
         CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[slot], 0));  // the chunk that used this slot is done
+        ctx->aux_recorded[slot] = false;
         RC(upload(slot, off, cnt));
         CU(cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_stream));
         return KZG_B200_OK;
@@ -416,18 +427,24 @@ static int staged_chunks(kzg_b200_ctx *ctx, size_t n, Upload upload, Run run, Fi
     // the slots may still be in use by an earlier asynchronous call on `stream`
     for (int sl = 0; sl < KZG_SLOTS; sl++) CU(cudaEventRecord(ctx->ev_free[sl], ctx->stream));
     for (size_t i = 0; i < std::min(ahead, nchunks); i++) RC(enqueue_upload(i));
+    lap("uploads");
     for (size_t i = 0; i < nchunks; i++) {
         int slot = (int)(i % KZG_SLOTS);
         size_t off = i * ctx->chunk, cnt = std::min(ctx->chunk, n - off);
         if (i + ahead < nchunks) RC(enqueue_upload(i + ahead));
         lane_select(ctx, i);
         CU(cudaStreamWaitEvent(ctx->cur->stream, ctx->ev_h2d[slot], 0));
-        RC(run(slot, off, cnt));
+        ctx->aux_ready = ctx->aux_recorded[slot] ? ctx->ev_aux[slot] : nullptr;
+        int run_rc = run(slot, off, cnt);
+        ctx->aux_ready = nullptr;
+        RC(run_rc);
         CU(cudaEventRecord(ctx->ev_free[slot], ctx->cur->stream));
     }
+    lap("enqueue");
     RC(lanes_end(ctx));
     RC(finish());
     CU(cudaStreamSynchronize(ctx->stream));
+    lap("wait");
     stage_collect(ctx);
     return KZG_B200_OK;
 }

@@ -40,11 +40,22 @@ static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t 
         // the caller validated the commitments (status already holds the verdicts) and hashed the challenges
         CU(cudaMemcpyAsync(ln->d_z, d_z_ready, count * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
     } else if (d_commitments) {
-        CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), st));
-        // small calls: the commitment check runs on the side stream beside the challenge hash and the evaluation
+        // small calls: the commitment check runs on the side stream beside the challenge hash and the evaluation.  When the
+        // commitments were uploaded ahead of the blobs (host calls), it starts as soon as they are there.
         side = count <= 256 && !ctx->profile;
-        if (side) RC(decode_points_side(ctx, d_commitments, ln->d_pts, d_status, count, 1, count));
-        else RC(decode_points(ctx, d_commitments, ln->d_pts, d_status, count, 1, count));
+        if (side && ctx->aux_ready) {
+            CU(cudaStreamWaitEvent(ln->side_stream, ctx->aux_ready, 0));
+            CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), ln->side_stream));
+            CU(cudaEventRecord(ln->ev_side_fork, ln->side_stream));
+            CU(cudaStreamWaitEvent(st, ln->ev_side_fork, 0));  // the status is zeroed before the evaluation may mark it
+            RC(g1_launch_decode(ln->side_stream, d_commitments, ln->d_pts, d_status, count, 1, count));
+            CU(cudaEventRecord(ln->ev_side_join, ln->side_stream));
+            ctx->launches++;
+        } else {
+            CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), st));
+            if (side) RC(decode_points_side(ctx, d_commitments, ln->d_pts, d_status, count, 1, count));
+            else RC(decode_points(ctx, d_commitments, ln->d_pts, d_status, count, 1, count));
+        }
         stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
         int rc = fr_launch_challenge(st, d_blobs, d_commitments, count, ctx->n, ln->d_z, ctx->call_blobs, ctx->sms);
         stage_end(ctx, 1);
@@ -120,8 +131,10 @@ extern "C" int kzg_b200_compute_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const ui
     return staged_chunks(
         ctx, n,
         [&](int slot, size_t off, size_t cnt) -> int {
-            CU(cudaMemcpyAsync(ctx->d_stage_in + slot * ch * bpb, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->copy_stream));
             CU(cudaMemcpyAsync(ctx->d_stage_aux + slot * ch * 96, commitments + off * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CU(cudaEventRecord(ctx->ev_aux[slot], ctx->copy_stream));
+            ctx->aux_recorded[slot] = true;
+            CU(cudaMemcpyAsync(ctx->d_stage_in + slot * ch * bpb, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->copy_stream));
             return KZG_B200_OK;
         },
         [&](int slot, size_t off, size_t cnt) -> int {
@@ -217,28 +230,56 @@ static int verify_chunk_a(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8
                           size_t off, size_t n_total, const VerifyBufs &vb, int32_t *d_st) {
     kzg_b200_ctx::Lane *ln = ctx->cur;
     cudaStream_t sm = ln->stream;
-    CU(cudaMemsetAsync(d_st, 0, cnt * sizeof(int32_t), sm));
+    // KZG_B200_TRACE=2: device timestamps of this chunk's steps (events on the lane's streams), printed by the next call
+    static cudaEvent_t tr[6];
+    static bool tr_init = false, tr_armed = false;
+    const bool tr_on = env_int("KZG_B200_TRACE", 0) == 2;
+    if (tr_on && !tr_init) { for (auto &e : tr) cudaEventCreate(&e); tr_init = true; }
+    if (tr_on && tr_armed) {
+        float a = 0, b = 0, c = 0, d = 0, e = 0;
+        cudaEventSynchronize(tr[5]);
+        cudaEventElapsedTime(&a, tr[0], tr[1]); cudaEventElapsedTime(&b, tr[1], tr[2]); cudaEventElapsedTime(&c, tr[2], tr[3]);
+        cudaEventElapsedTime(&d, tr[3], tr[5]); cudaEventElapsedTime(&e, tr[0], tr[4]);
+        fprintf(stderr, "[kzg_b200 trace] chunk A: memset %.3f, hash %.3f, eval %.3f, join %.3f ms; validation done at %.3f ms\n", a, b, c, d, e);
+    }
+    if (tr_on) cudaEventRecord(tr[0], sm);
     const bool side = !ctx->profile;  // profiling keeps the stages apart
     cudaStream_t sd = side ? ln->side_stream : sm;
-    if (side) {
-        CU(cudaEventRecord(ln->ev_side_fork, sm));
-        CU(cudaStreamWaitEvent(sd, ln->ev_side_fork, 0));
+    if (side && ctx->aux_ready) {
+        // host calls: the commitments and proofs of the slot were uploaded ahead of its blobs.  The validation starts as
+        // soon as they are there -- under the upload of the blobs -- and therefore never at the same instant as the hash:
+        // two latency-bound launches released by the same event were placed on the same SMs every other call (device
+        // timestamps of a six-blob call: hash 2.03 / validation 1.71 ms apart, 2.43 / 3.12 ms together).
+        CU(cudaStreamWaitEvent(sd, ctx->aux_ready, 0));
+        CU(cudaMemsetAsync(d_st, 0, cnt * sizeof(int32_t), sd));
+        CU(cudaEventRecord(ln->ev_side_fork, sd));
+        CU(cudaStreamWaitEvent(sm, ln->ev_side_fork, 0));  // the status is zeroed before the evaluation may mark it
+    } else {
+        CU(cudaMemsetAsync(d_st, 0, cnt * sizeof(int32_t), sm));
+        if (side) {
+            CU(cudaEventRecord(ln->ev_side_fork, sm));
+            CU(cudaStreamWaitEvent(sd, ln->ev_side_fork, 0));
+        }
     }
     stage_begin(ctx, KZG_B200_STAGE_VALIDATE);
     int rc = g1_launch_decode2(sd, d_commitments, d_proofs, vb.pts + off, vb.pts + n_total + off, d_st, cnt, 1);
     stage_end(ctx, 1);
     RC(rc);
     if (side) CU(cudaEventRecord(ln->ev_side_join, sd));
+    if (tr_on) { cudaEventRecord(tr[4], sd); cudaEventRecord(tr[1], sm); }
     stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
     rc = fr_launch_challenge(sm, d_blobs, d_commitments, cnt, ctx->n, ln->d_z, ctx->call_blobs, ctx->sms);
     stage_end(ctx, 1);
     RC(rc);
+    if (tr_on) cudaEventRecord(tr[2], sm);
     stage_begin(ctx, KZG_B200_STAGE_EVAL);
     rc = fr_launch_eval(sm, 0, d_blobs, ln->d_z, ctx->d_roots, ctx->n, ln->d_inv, ln->d_poly, vb.zy + 64 * off, d_st, cnt);
     stage_end(ctx, 1);
     ctx->launches += 3;
     RC(rc);
+    if (tr_on) cudaEventRecord(tr[3], sm);
     if (side) CU(cudaStreamWaitEvent(sm, ln->ev_side_join, 0));
+    if (tr_on) { cudaEventRecord(tr[5], sm); tr_armed = true; }
     return KZG_B200_OK;
 }
 
@@ -255,9 +296,11 @@ static int verify_phase_a_locked(kzg_b200_ctx *ctx, const uint8_t *blobs, const 
         ctx, n,
         [&](int slot, size_t off, size_t cnt) -> int {
             uint8_t *aux = ctx->d_stage_aux + slot * ch * 96;
-            CU(cudaMemcpyAsync(ctx->d_stage_in + slot * ch * bpb, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->copy_stream));
             CU(cudaMemcpyAsync(aux, commitments + off * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->copy_stream));
             CU(cudaMemcpyAsync(aux + cnt * 48, proofs + off * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CU(cudaEventRecord(ctx->ev_aux[slot], ctx->copy_stream));
+            ctx->aux_recorded[slot] = true;
+            CU(cudaMemcpyAsync(ctx->d_stage_in + slot * ch * bpb, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->copy_stream));
             return KZG_B200_OK;
         },
         [&](int slot, size_t off, size_t cnt) -> int {

@@ -21,8 +21,8 @@ L.kzg_b200_synchronize(s._h)
 pin = lambda t_: torch.empty(t_.shape, dtype=t_.dtype, pin_memory=True).copy_(t_).numpy()
 vb, vc, vp = pin(blobs.reshape(n, 131072)), pin(cm), pin(pr)
 ok = ctypes.c_int(0)
-for m in (256, 1024, 2048, 4096):
-    for form in ("0", "1", "2", "4", "8", "16", "32"):
+for m in (6, 64, 256, 1024, 2048, 4096):
+    for form in (os.environ.get("AB_FORMS", "0,1,2,4,8,16,32").split(",")):
         if int(form) * m > 32 * 2400:
             continue
         os.environ["KZG_B200_CHALLENGE_G"] = form
@@ -31,7 +31,7 @@ for m in (256, 1024, 2048, 4096):
                    lambda: L.kzg_b200_verify_blob_kzg_proof_batch_device(s._h, blobs.data_ptr(), cm.data_ptr(), pr.data_ptr(), m, ctypes.byref(ok))):
             fn()
             ts = []
-            for _ in range(5):
+            for _ in range(8):
                 t = time.perf_counter(); fn(); ts.append((time.perf_counter() - t) * 1e3)
-            res.append(min(ts))
-        print("n=%5d G=%2s  host %.2f ms  device %.2f ms" % (m, form, res[0], res[1]), flush=True)
+            res.append((min(ts), sum(ts) / len(ts)))
+        print("n=%5d G=%2s  host %.2f ms (mean %.2f)  device %.2f ms (mean %.2f)" % (m, form, res[0][0], res[0][1], res[1][0], res[1][1]), flush=True)

@@ -19,7 +19,7 @@ pin = lambda a: torch.empty(a.shape, dtype=torch.uint8, pin_memory=True).copy_(t
 vb, vc, vp = pin(blobs), pin(cms), pin(prs)
 for _ in range(3):
     assert k.Kzg.verify_blob_kzg_proof_batch_raw(vb, vc, vp, n, s)
-os.environ["KZG_B200_TRACE"] = "1"
+os.environ["KZG_B200_TRACE"] = sys.argv[2] if len(sys.argv) > 2 else "1"
 for _ in range(3):
     t = time.perf_counter()
     assert k.Kzg.verify_blob_kzg_proof_batch_raw(vb, vc, vp, n, s)
