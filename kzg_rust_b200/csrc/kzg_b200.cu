@@ -406,7 +406,7 @@ static int staged_chunks(kzg_b200_ctx *ctx, size_t n, Upload upload, Run run, Fi
     const size_t nchunks = (n + ctx->chunk - 1) / ctx->chunk;
     const size_t ahead = KZG_SLOTS - 1;
     ctx->call_blobs = n;
-    const bool trace = env_int("KZG_B200_TRACE", 0) == 3;  // host wall clock of the enqueue / wait phases on stderr
+    const bool trace = env_int("KZG_B200_TRACE", 0) == 2;  // host wall clock of the enqueue / wait phases on stderr
     auto t0 = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
         if (!trace) return;

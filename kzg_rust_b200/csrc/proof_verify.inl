@@ -230,19 +230,6 @@ static int verify_chunk_a(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8
                           size_t off, size_t n_total, const VerifyBufs &vb, int32_t *d_st) {
     kzg_b200_ctx::Lane *ln = ctx->cur;
     cudaStream_t sm = ln->stream;
-    // KZG_B200_TRACE=2: device timestamps of this chunk's steps (events on the lane's streams), printed by the next call
-    static cudaEvent_t tr[6];
-    static bool tr_init = false, tr_armed = false;
-    const bool tr_on = env_int("KZG_B200_TRACE", 0) == 2;
-    if (tr_on && !tr_init) { for (auto &e : tr) cudaEventCreate(&e); tr_init = true; }
-    if (tr_on && tr_armed) {
-        float a = 0, b = 0, c = 0, d = 0, e = 0;
-        cudaEventSynchronize(tr[5]);
-        cudaEventElapsedTime(&a, tr[0], tr[1]); cudaEventElapsedTime(&b, tr[1], tr[2]); cudaEventElapsedTime(&c, tr[2], tr[3]);
-        cudaEventElapsedTime(&d, tr[3], tr[5]); cudaEventElapsedTime(&e, tr[0], tr[4]);
-        fprintf(stderr, "[kzg_b200 trace] chunk A: memset %.3f, hash %.3f, eval %.3f, join %.3f ms; validation done at %.3f ms\n", a, b, c, d, e);
-    }
-    if (tr_on) cudaEventRecord(tr[0], sm);
     const bool side = !ctx->profile;  // profiling keeps the stages apart
     cudaStream_t sd = side ? ln->side_stream : sm;
     if (side && ctx->aux_ready) {
@@ -266,20 +253,16 @@ static int verify_chunk_a(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8
     stage_end(ctx, 1);
     RC(rc);
     if (side) CU(cudaEventRecord(ln->ev_side_join, sd));
-    if (tr_on) { cudaEventRecord(tr[4], sd); cudaEventRecord(tr[1], sm); }
     stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
     rc = fr_launch_challenge(sm, d_blobs, d_commitments, cnt, ctx->n, ln->d_z, ctx->call_blobs, ctx->sms);
     stage_end(ctx, 1);
     RC(rc);
-    if (tr_on) cudaEventRecord(tr[2], sm);
     stage_begin(ctx, KZG_B200_STAGE_EVAL);
     rc = fr_launch_eval(sm, 0, d_blobs, ln->d_z, ctx->d_roots, ctx->n, ln->d_inv, ln->d_poly, vb.zy + 64 * off, d_st, cnt);
     stage_end(ctx, 1);
     ctx->launches += 3;
     RC(rc);
-    if (tr_on) cudaEventRecord(tr[3], sm);
     if (side) CU(cudaStreamWaitEvent(sm, ln->ev_side_join, 0));
-    if (tr_on) { cudaEventRecord(tr[5], sm); tr_armed = true; }
     return KZG_B200_OK;
 }
 
@@ -465,7 +448,7 @@ extern "C" int kzg_b200_verify_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const uin
     std::vector<uint8_t> zy(n * 64);
     VerifyBufs vb;
     // KZG_B200_TRACE=1: wall-clock milliseconds of the host-visible steps on stderr (tools/verify_stages.py)
-    const bool trace = env_int("KZG_B200_TRACE", 0) != 0;
+    const bool trace = env_int("KZG_B200_TRACE", 0) != 0;  // 2: also the enqueue / wait phases of the staged chunks
     auto t0 = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
         if (!trace) return;
