@@ -13,7 +13,7 @@ int fr_setup_roots_device(int n, fr_t **d_roots, cudaStream_t stream) { return f
 template <int G>
 static void launch_challenge_group(cudaStream_t st, const uint8_t *d_blobs, const uint8_t *d_commitments, size_t count, int n, fr_t *d_z) {
     const size_t warps = (count * G + 31) / 32;
-    k_challenge_group<G><<<blocks_for(warps, 4), 128, 0, st>>>(d_blobs, d_commitments, (uint32_t)count, n, d_z);
+    k_challenge_group<G><<<blocks_for(warps, 4), 128, 0, st>>>(d_blobs, d_commitments, (uint32_t)count, n, d_z, 1u);
 }
 // The most lanes per blob that still leave every warp of the launch a scheduler of its own (frpath.cuh).  The validation of
 // the chunk's points (`beside` blocks of four warps, one thread per point) runs beside the hash and is just as latency-bound:
@@ -27,11 +27,14 @@ static int challenge_lanes_per_blob(size_t count, size_t call_blobs, size_t besi
     while (g > 1 && (count * g + 127) / 128 > budget) g >>= 1;
     return g;
 }
+int fr_challenge_form(size_t count, size_t call_blobs, int sms) {
+    const int g = env_int("KZG_B200_CHALLENGE_G", 0);  // forces a form
+    return g > 0 ? g : challenge_lanes_per_blob(count, call_blobs, (2 * count + 127) / 128, sms);
+}
 int fr_launch_challenge(cudaStream_t st, const uint8_t *d_blobs, const uint8_t *d_commitments, size_t count, int n, fr_t *d_z,
                         size_t call_blobs, int sms) {
     if (count == 0) return KZG_B200_OK;
-    int g = env_int("KZG_B200_CHALLENGE_G", 0);  // forces a form
-    if (g <= 0) g = challenge_lanes_per_blob(count, call_blobs, (2 * count + 127) / 128, sms);
+    const int g = fr_challenge_form(count, call_blobs, sms);
     switch (g) {
         case 32: launch_challenge_group<32>(st, d_blobs, d_commitments, count, n, d_z); break;
         case 16: launch_challenge_group<16>(st, d_blobs, d_commitments, count, n, d_z); break;

@@ -159,8 +159,9 @@ KZG_D uint32_t challenge_msg_word(const uint8_t *__restrict__ blob, const uint8_
 // one block of four warps; kw: 4 x 64 x 32 words of shared memory
 template <int G>
 KZG_D void challenge_group_block(uint32_t (*kw)[64 * 32], uint32_t block, const uint8_t *__restrict__ blobs,
-                                 const uint8_t *__restrict__ commitments, uint32_t count, int n, fr_t *__restrict__ z_out) {
+                                 const uint8_t *__restrict__ commitments, uint32_t count, int n, fr_t *__restrict__ z_out, uint32_t one) {
     constexpr uint32_t K[64] = {KZG_SHA256_K};
+    auto fadd = [one](uint32_t x, uint32_t y) -> uint32_t { return sha_fadd(x, y, one); };  // an IMAD (FMA pipe), see sha256.cuh
     constexpr uint32_t PER_WARP = 32 / G;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, slot = lane / G, sub = lane % G;
     if ((block * 4 + warp) * PER_WARP >= count) return;  // the whole warp
@@ -211,12 +212,15 @@ KZG_D void challenge_group_block(uint32_t (*kw)[64 * 32], uint32_t block, const 
                 // A scheduler that carries one warp runs one dependent chain, so the depth of a round counts too:
                 // h + K + W and d + h + K + W do not depend on this round's e, which leaves rotate -> xor -> ONE
                 // three-input add on the path from e to the next e (and from a to the next a).
-                const uint32_t hkw = hh + mine[t * 32 + col], dhkw = d + hkw;
+                // The rotations and the boolean functions (10 instructions per round) go to the 16-lane integer pipe, 2 cycles
+                // each.  The two sums on the dependent path (e -> next e, a -> next a) are one three-input add each; the
+                // others are written as multiply-adds by a run-time 1 so that they issue on the FMA pipe beside them.
+                const uint32_t hkw = fadd(hh, mine[t * 32 + col]), dhkw = fadd(d, hkw);
                 const uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
                 const uint32_t ch = (e & f) ^ (~e & g);
                 const uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
                 const uint32_t mj = (a & bb) ^ (a & c) ^ (bb & c);
-                const uint32_t t1 = hkw + S1 + ch;
+                const uint32_t t1 = fadd(hkw, fadd(S1, ch));
                 hh = g; g = f; f = e; e = dhkw + S1 + ch; d = c; c = bb; bb = a; a = t1 + S0 + mj;
             }
             h[0] += a; h[1] += bb; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
@@ -233,9 +237,9 @@ KZG_D void challenge_group_block(uint32_t (*kw)[64 * 32], uint32_t block, const 
 }
 template <int G>
 __global__ void __launch_bounds__(128) k_challenge_group(const uint8_t *__restrict__ blobs, const uint8_t *__restrict__ commitments,
-                                                         uint32_t count, int n, fr_t *__restrict__ z_out) {
+                                                         uint32_t count, int n, fr_t *__restrict__ z_out, uint32_t one) {
     __shared__ uint32_t kw[4][64 * 32];  // [round t][lane]: conflict-free writes; reads are broadcasts inside a blob's lanes
-    challenge_group_block<G>(kw, blockIdx.x, blobs, commitments, count, n, z_out);
+    challenge_group_block<G>(kw, blockIdx.x, blobs, commitments, count, n, z_out, one);
 }
 // caller-supplied evaluation points (compute_kzg_proof): 32 big-endian bytes each, must be
 // canonical (reference src/kzg.rs:452 -> bytes_to_bls_field)

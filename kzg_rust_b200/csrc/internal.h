@@ -106,6 +106,9 @@ struct kzg_b200_ctx {
     size_t sums_all_elems = 0;
     kzg::fr_t *d_z_all = nullptr;          // challenges of a whole device-resident call (grow-only)
     size_t z_all_elems = 0;
+    uint8_t *h_pin = nullptr;         // pinned host buffer of a device-resident verification call (grow-only)
+    size_t h_pin_bytes = 0;
+    std::vector<cudaEvent_t> ev_chunks;  // "this chunk's (z, y) records are on the host", one per chunk of such a call
     uint8_t *d_vb = nullptr;          // buffers of one verification call (grow-only)
     size_t vb_bytes = 0;
     // what the last kzg_b200_verify_phase_a validated and left decoded in d_vb: SHA-256 over (n, commitments, proofs).
@@ -162,6 +165,9 @@ int g1_launch_tau_identity(cudaStream_t st, const uint8_t *d_commitments, const 
 
 // ---- frops.cu
 int fr_setup_roots_device(int n, kzg::fr_t **d_roots, cudaStream_t stream);
+// lanes per blob the hash of `count` blobs will use (1 = one thread per blob: the batch is too large for hash and validation
+// to have a scheduler per warp)
+int fr_challenge_form(size_t count, size_t call_blobs, int sms);
 // call_blobs: blobs of the whole call this launch is a chunk of (picks the form of the hash kernel)
 int fr_launch_challenge(cudaStream_t st, const uint8_t *d_blobs, const uint8_t *d_commitments, size_t count, int n, kzg::fr_t *d_z,
                         size_t call_blobs, int sms);

@@ -246,6 +246,8 @@ extern "C" void kzg_b200_ctx_destroy(kzg_b200_ctx *ctx) {
     if (ctx->lanes[1].stream) cudaStreamSynchronize(ctx->lanes[1].stream);
     free_workspace(ctx);
     cudaFree(ctx->d_vb);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    for (cudaEvent_t e : ctx->ev_chunks) cudaEventDestroy(e);
     cudaFree(ctx->d_z_all);
     cudaFree(ctx->d_sums_all);
     cudaFree(ctx->d_table);

@@ -324,28 +324,37 @@ extern "C" int kzg_b200_verify_phase_a(kzg_b200_ctx *ctx, const uint8_t *blobs, 
 
 // reference compute_r_powers (src/utils.rs:426-474), the hash only: the points are hashed in
 // their compressed form, which for a validated point is the caller's own 48 bytes.
-extern "C" int kzg_b200_compute_r(const kzg_b200_ctx *ctx, const uint8_t *commitments, const uint8_t *zy,
-                                  const uint8_t *proofs, size_t n_total, uint8_t r_out[32]) {
-    if (!ctx || !r_out || (n_total && (!commitments || !zy || !proofs))) return KZG_B200_BAD_ARGS;
-    HostSha256 h;
+static void compute_r_begin(HostSha256 &h, uint64_t field_elements, uint64_t n_total) {
     h.init();
     h.update((const uint8_t *)"RCKZGBATCH___V1_", 16);
     uint8_t u[8];
-    for (int i = 0; i < 8; i++) u[i] = (uint8_t)((uint64_t)ctx->n >> (56 - 8 * i));
+    for (int i = 0; i < 8; i++) u[i] = (uint8_t)(field_elements >> (56 - 8 * i));
     h.update(u, 8);
-    for (int i = 0; i < 8; i++) u[i] = (uint8_t)((uint64_t)n_total >> (56 - 8 * i));
+    for (int i = 0; i < 8; i++) u[i] = (uint8_t)(n_total >> (56 - 8 * i));
     h.update(u, 8);
-    for (size_t i = 0; i < n_total; i++) {
+}
+static void compute_r_update(HostSha256 &h, const uint8_t *commitments, const uint8_t *zy, const uint8_t *proofs, size_t count) {
+    for (size_t i = 0; i < count; i++) {
         h.update(commitments + 48 * i, 48);
         h.update(zy + 64 * i, 64);
         h.update(proofs + 48 * i, 48);
     }
+}
+static void compute_r_finish(HostSha256 &h, uint8_t r_out[32]) {
     uint8_t d[32];
     h.finish(d);
     fr_t r;
     scalar_from_be32(r, d);
     scalar_reduce(r);
     scalar_to_be32(r_out, r);
+}
+extern "C" int kzg_b200_compute_r(const kzg_b200_ctx *ctx, const uint8_t *commitments, const uint8_t *zy,
+                                  const uint8_t *proofs, size_t n_total, uint8_t r_out[32]) {
+    if (!ctx || !r_out || (n_total && (!commitments || !zy || !proofs))) return KZG_B200_BAD_ARGS;
+    HostSha256 h;
+    compute_r_begin(h, (uint64_t)ctx->n, n_total);
+    compute_r_update(h, commitments, zy, proofs, n_total);
+    compute_r_finish(h, r_out);
     return KZG_B200_OK;
 }
 
@@ -494,39 +503,87 @@ extern "C" int kzg_b200_verify_blob_kzg_proof_batch_device(kzg_b200_ctx *ctx, co
     kzg_b200_ctx::Lane *ln = ctx->cur = &ctx->lanes[0];
     cudaStream_t sm = ctx->stream, sd = ctx->profile ? sm : ln->side_stream;
     CU(cudaMemsetAsync(vb.status, 0, n * sizeof(int32_t), sm));
-    CU(cudaEventRecord(ln->ev_side_fork, sm));
-    CU(cudaStreamWaitEvent(sd, ln->ev_side_fork, 0));
-    stage_begin(ctx, KZG_B200_STAGE_VALIDATE);
-    int rc = g1_launch_decode2(sd, d_commitments, d_proofs, vb.pts, vb.pts + n, vb.status, n, 1);
-    stage_end(ctx, 1);
-    RC(rc);
-    CU(cudaEventRecord(ln->ev_side_join, sd));
+    // Where the validation of the 2n points runs: beside the hash while both fit one warp per scheduler (up to ~4,700 blobs);
+    // for larger calls beside the evaluation, after the hash -- two latency-bound kernels that share schedulers cost far more
+    // than they overlap (tools/order_ab.py: 8,192 blobs 21.1 ms beside the hash, 14.0 ms beside the evaluation).
+    const int order = fr_challenge_form(n, n, ctx->sms) >= 2 ? 0 : 2;
+    int rc;
+    auto validate = [&](cudaStream_t s_) -> int {
+        stage_begin(ctx, KZG_B200_STAGE_VALIDATE);
+        int vrc = g1_launch_decode2(s_, d_commitments, d_proofs, vb.pts, vb.pts + n, vb.status, n, 1);
+        stage_end(ctx, 1);
+        return vrc;
+    };
+    if (order != 2) {
+        CU(cudaEventRecord(ln->ev_side_fork, sm));
+        CU(cudaStreamWaitEvent(sd, ln->ev_side_fork, 0));
+        RC(validate(sd));
+        CU(cudaEventRecord(ln->ev_side_join, sd));
+    }
     stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
     rc = fr_launch_challenge(sm, d_blobs, d_commitments, n, ctx->n, ctx->d_z_all, n, ctx->sms);
     stage_end(ctx, 1);
     RC(rc);
+    if (order == 2) {
+        CU(cudaEventRecord(ln->ev_side_fork, sm));
+        CU(cudaStreamWaitEvent(sd, ln->ev_side_fork, 0));
+        RC(validate(sd));
+        CU(cudaEventRecord(ln->ev_side_join, sd));
+    }
     ctx->launches += 2;
+    // The sequential hash of compute_r_powers (160 bytes per blob, host) runs chunk by chunk while the GPU evaluates the
+    // next chunk: every chunk's (z, y) records come back to pinned memory behind their own event.
+    const size_t nchunks = (n + ctx->chunk - 1) / ctx->chunk, pin_need = n * (64 + 48 + 48 + sizeof(int32_t));
+    if (pin_need > ctx->h_pin_bytes) {
+        if (ctx->h_pin) CU(cudaFreeHost(ctx->h_pin));
+        ctx->h_pin = nullptr;
+        ctx->h_pin_bytes = 0;
+        CU(cudaHostAlloc((void **)&ctx->h_pin, pin_need + pin_need / 2, cudaHostAllocDefault));
+        ctx->h_pin_bytes = pin_need + pin_need / 2;
+    }
+    while (ctx->ev_chunks.size() < nchunks + 1) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_chunks.push_back(e);
+    }
+    uint8_t *h_zy = ctx->h_pin, *h_cm = h_zy + 64 * n, *h_pr = h_cm + 48 * n;
+    int32_t *h_st = reinterpret_cast<int32_t *>(h_pr + 48 * n);
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ln->ev_side_fork, 0));  // after whatever preceded this call on the stream
+    CU(cudaMemcpyAsync(h_cm, d_commitments, n * 48, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU(cudaMemcpyAsync(h_pr, d_proofs, n * 48, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU(cudaEventRecord(ctx->ev_chunks[nchunks], ctx->copy_stream));
     stage_begin(ctx, KZG_B200_STAGE_EVAL);
     uint64_t evals = 0;
     for (size_t off = 0; off < n; off += ctx->chunk, evals++) {
         const size_t cnt = std::min(ctx->chunk, n - off);
         RC(fr_launch_eval(sm, 0, d_blobs + off * bpb, ctx->d_z_all + off, ctx->d_roots, ctx->n, ln->d_inv, ln->d_poly, vb.zy + 64 * off,
                           vb.status + off, cnt));
+        if (!ctx->profile) {
+            CU(cudaMemcpyAsync(h_zy + 64 * off, vb.zy + 64 * off, cnt * 64, cudaMemcpyDeviceToHost, sm));
+            CU(cudaEventRecord(ctx->ev_chunks[evals], sm));
+        }
     }
     stage_end(ctx, evals);
     ctx->launches += evals;
+    if (ctx->profile) {  // the stage timers own the stream's event order: one copy at the end
+        CU(cudaMemcpyAsync(h_zy, vb.zy, n * 64, cudaMemcpyDeviceToHost, sm));
+        for (size_t c = 0; c < nchunks; c++) CU(cudaEventRecord(ctx->ev_chunks[c], sm));
+    }
     CU(cudaStreamWaitEvent(sm, ln->ev_side_join, 0));
-    std::vector<uint8_t> zy(n * 64), cm(n * 48), pr(n * 48);
-    std::vector<int32_t> st(n);
-    CU(cudaMemcpyAsync(zy.data(), vb.zy, n * 64, cudaMemcpyDeviceToHost, sm));
-    CU(cudaMemcpyAsync(cm.data(), d_commitments, n * 48, cudaMemcpyDeviceToHost, sm));
-    CU(cudaMemcpyAsync(pr.data(), d_proofs, n * 48, cudaMemcpyDeviceToHost, sm));
-    CU(cudaMemcpyAsync(st.data(), vb.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, sm));
+    CU(cudaMemcpyAsync(h_st, vb.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, sm));
+    HostSha256 hs;
+    compute_r_begin(hs, (uint64_t)ctx->n, n);
+    CU(cudaEventSynchronize(ctx->ev_chunks[nchunks]));
+    for (size_t c = 0; c < nchunks; c++) {
+        const size_t off = c * ctx->chunk, cnt = std::min(ctx->chunk, n - off);
+        CU(cudaEventSynchronize(ctx->ev_chunks[c]));
+        compute_r_update(hs, h_cm + 48 * off, h_zy + 64 * off, h_pr + 48 * off, cnt);
+    }
     CU(cudaStreamSynchronize(sm));
     for (size_t i = 0; i < n; i++)
-        if (st[i] != KZG_B200_OK) return KZG_B200_BAD_ARGS;
+        if (h_st[i] != KZG_B200_OK) return KZG_B200_BAD_ARGS;
     uint8_t r[32], partial[224];
-    RC(kzg_b200_compute_r(ctx, cm.data(), zy.data(), pr.data(), n, r));
+    compute_r_finish(hs, r);
     RC(verify_phase_b_device(ctx, vb, n, n, r, 0, partial));
     return host_verify_finish(partial, 1, ctx->tau_prepared, ok) == 0 ? KZG_B200_OK : KZG_B200_BAD_ARGS;
 }

@@ -31,8 +31,23 @@ KZG_HD void sha256_init(uint32_t h[8]) {
     h[4] = 0x510e527fu; h[5] = 0x9b05688cu; h[6] = 0x1f83d9abu; h[7] = 0x5be0cd19u;
 }
 
+// x + y as x * one + y with a run-time one = 1: on the device that is an IMAD, which issues on the FMA pipe, where a plain
+// addition would queue on the 16-lane integer pipe behind the rotations and boolean functions that bound a hash stream.
+KZG_HD uint32_t sha_fadd(uint32_t x, uint32_t y, uint32_t one) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(one), "r"(y));
+    return r;
+#else
+    (void)one;
+    return x + y;
+#endif
+}
+
 // One compression.  w[16] is clobbered (it is the rolling message schedule).  Fully
 // unrolled so that w[] and the round constants stay in registers / immediates.
+// (With one stream per thread the plain additions are the faster form: written as IMADs the compression of 16,384 streams
+// took 4.18 ms instead of 3.80 ms.  The grouped kernel, where a scheduler carries one warp, gains from them: frpath.cuh.)
 KZG_HD void sha256_compress(uint32_t h[8], uint32_t w[16]) {
     constexpr uint32_t K[64] = {KZG_SHA256_K};
     uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
