@@ -175,7 +175,7 @@ enum {
     KZG_B200_STAGE_CHALLENGE = 4,    /* per-blob SHA-256 Fiat-Shamir challenge */
     KZG_B200_STAGE_EVAL = 5,         /* barycentric evaluation (+ quotient, digits) */
     KZG_B200_STAGE_VALIDATE = 6,     /* G1 decompression + subgroup checks */
-    KZG_B200_STAGE_VERIFY_TERMS = 7, /* r-power scalar multiplications of batch verification */
+    KZG_B200_STAGE_VERIFY_TERMS = 7, /* r-power linear combinations of batch verification (bucket-method MSM) */
     KZG_B200_NUM_STAGES = 8
 };
 int kzg_b200_profile_enable(kzg_b200_ctx *ctx, int on);
