@@ -19,11 +19,14 @@ static void launch_challenge_group(cudaStream_t st, const uint8_t *d_blobs, cons
 // the chunk's points (`beside` blocks of four warps, one thread per point) runs beside the hash and is just as latency-bound:
 // as long as both together have at most one block per SM, no scheduler carries two warps.  (Measured on whole calls,
 // tools/hash_form_ab.py: a hash block sharing an SM with a validation block runs 1.5 - 2x longer.)
-// A chunk of a larger call (call_blobs > count) runs beside the other lane's kernels, where instructions per blob count
-// and latency does not: one thread per blob.
+// A chunk of a larger call (call_blobs > count) runs beside the other lane's chunk and gets half of the SMs; the 4,096-blob
+// chunks of the proof path end at one thread per blob that way (where instructions per blob count and latency does not), the
+// 1,024-blob chunks of host verification at four lanes per blob.
 static int challenge_lanes_per_blob(size_t count, size_t call_blobs, size_t beside, int sms) {
-    const size_t budget = (size_t)sms > beside ? (size_t)sms - beside : 0;
-    int g = call_blobs > count ? 1 : 32;
+    // a chunk of a larger call shares the GPU with the other lane's chunk: half of the SMs each
+    const size_t mine = call_blobs > count ? (size_t)sms / 2 : (size_t)sms;
+    const size_t budget = mine > beside ? mine - beside : 0;
+    int g = 32;
     while (g > 1 && (count * g + 127) / 128 > budget) g >>= 1;
     return g;
 }

@@ -403,9 +403,11 @@ extern "C" int kzg_b200_blob_to_kzg_commitment_device(kzg_b200_ctx *ctx, const u
 // upload(slot, off, cnt) enqueues the H2D copies of one chunk on copy_stream; run(slot, off, cnt)
 // enqueues kernels + D2H on the current lane's stream.
 // finish() runs once after the lanes have joined, on the caller-visible stream, before the call waits for it.
+// piece: blobs per chunk of this call (at most ctx->chunk, the size of a staging slot).
 template <class Upload, class Run, class Finish>
-static int staged_chunks(kzg_b200_ctx *ctx, size_t n, Upload upload, Run run, Finish finish) {
-    const size_t nchunks = (n + ctx->chunk - 1) / ctx->chunk;
+static int staged_chunks(kzg_b200_ctx *ctx, size_t n, size_t piece, Upload upload, Run run, Finish finish) {
+    piece = std::max<size_t>(1, std::min(piece, ctx->chunk));
+    const size_t nchunks = (n + piece - 1) / piece;
     const size_t ahead = KZG_SLOTS - 1;
     ctx->call_blobs = n;
     const bool trace = env_int("KZG_B200_TRACE", 0) == 2;  // host wall clock of the enqueue / wait phases on stderr
@@ -418,7 +420,7 @@ static int staged_chunks(kzg_b200_ctx *ctx, size_t n, Upload upload, Run run, Fi
     };
     auto enqueue_upload = [&](size_t i) -> int {
         int slot = (int)(i % KZG_SLOTS);
-        size_t off = i * ctx->chunk, cnt = std::min(ctx->chunk, n - off);
+        size_t off = i * piece, cnt = std::min(piece, n - off);
         CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[slot], 0));  // the chunk that used this slot is done
         ctx->aux_recorded[slot] = false;
         RC(upload(slot, off, cnt));
@@ -432,7 +434,7 @@ static int staged_chunks(kzg_b200_ctx *ctx, size_t n, Upload upload, Run run, Fi
     lap("uploads");
     for (size_t i = 0; i < nchunks; i++) {
         int slot = (int)(i % KZG_SLOTS);
-        size_t off = i * ctx->chunk, cnt = std::min(ctx->chunk, n - off);
+        size_t off = i * piece, cnt = std::min(piece, n - off);
         if (i + ahead < nchunks) RC(enqueue_upload(i + ahead));
         lane_select(ctx, i);
         CU(cudaStreamWaitEvent(ctx->cur->stream, ctx->ev_h2d[slot], 0));
@@ -451,8 +453,18 @@ static int staged_chunks(kzg_b200_ctx *ctx, size_t n, Upload upload, Run run, Fi
     return KZG_B200_OK;
 }
 template <class Upload, class Run>
-static int staged_chunks(kzg_b200_ctx *ctx, size_t n, Upload upload, Run run) {
-    return staged_chunks(ctx, n, upload, run, []() -> int { return KZG_B200_OK; });
+static int staged_chunks(kzg_b200_ctx *ctx, size_t n, size_t piece, Upload upload, Run run) {
+    return staged_chunks(ctx, n, piece, upload, run, []() -> int { return KZG_B200_OK; });
+}
+// grow-only pinned host buffer of the context (results that the host reads while the GPU works on the next chunk)
+static int ensure_pinned(kzg_b200_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->h_pin_bytes) return KZG_B200_OK;
+    if (ctx->h_pin) CU(cudaFreeHost(ctx->h_pin));
+    ctx->h_pin = nullptr;
+    ctx->h_pin_bytes = 0;
+    CU(cudaHostAlloc((void **)&ctx->h_pin, bytes + bytes / 2, cudaHostAllocDefault));
+    ctx->h_pin_bytes = bytes + bytes / 2;
+    return KZG_B200_OK;
 }
 
 extern "C" int kzg_b200_blob_to_kzg_commitment_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, size_t n, uint8_t *out,
@@ -465,7 +477,7 @@ extern "C" int kzg_b200_blob_to_kzg_commitment_batch(kzg_b200_ctx *ctx, const ui
     DeferredCompress dc;
     RC(deferred_begin(ctx, n, &dc));
     return staged_chunks(
-        ctx, n,
+        ctx, n, ch,
         [&](int slot, size_t off, size_t cnt) -> int {
             CU(cudaMemcpyAsync(ctx->d_stage_in + slot * ch * bpb, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->copy_stream));
             return KZG_B200_OK;
