@@ -396,7 +396,14 @@ def main():
             if rank == world - 1:
                 sp_bad[[0, 1]] = sp_bad[[1, 0]]
             tampered = sharded.verify_blob_kzg_proof_batch_sharded(be, sb, sc, sp_bad, n_tot, device=dev)
+            # the same with every rank's shard resident in its GPU's memory (no upload in phase A)
+            db, dc, dp = blobs[vlo:vhi], out[vlo:vhi], proofs[vlo:vhi]
+            good_d = sharded.verify_blob_kzg_proof_batch_sharded_device(be, db, dc, dp, n_tot, dev)
+            vms_d = timed_wall(lambda: sharded.verify_blob_kzg_proof_batch_sharded_device(be, db, dc, dp, n_tot, dev), 2)
+            if not good_d:
+                raise SystemExit("sharded verification (device-resident shards) gave the wrong verdict")
             verify_sharded = {"blobs": n_tot, "gpus": world, "ms_per_verdict": vms, "blobs_per_s": n_tot / (vms * 1e-3),
+                              "device_resident_shards": {"ms_per_verdict": vms_d, "blobs_per_s": n_tot / (vms_d * 1e-3)},
                               "accepted": bool(good), "tampered_rejected": not tampered,
                               "exchange": "2 all_gathers per verdict: 160 B per blob (C, z, y, proof) + status, then 225 B per rank",
                               "timing": "wall clock around the blocking call (it ends with a host pairing), max over ranks"}

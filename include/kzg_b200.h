@@ -161,6 +161,13 @@ int kzg_b200_synchronize(kzg_b200_ctx *ctx);
  * Fiat-Shamir challenges of the call run in one launch each. */
 int kzg_b200_verify_blob_kzg_proof_batch_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments,
                                                 const uint8_t *d_proofs, size_t n, int *ok);
+/* Phase A of the two-phase form (kzg_b200_verify_phase_a above) for a shard that is already in this context's GPU memory:
+ * zy_out (host, n x 64 B) as there; commitments_out / proofs_out (host, n x 48 B each, optional) receive the shard's
+ * compressed points, which the caller needs on the host for the exchange and for kzg_b200_compute_r.  Synchronous.
+ * kzg_b200_verify_phase_b on the same bytes reuses the points this call validated. */
+int kzg_b200_verify_phase_a_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments,
+                                   const uint8_t *d_proofs, size_t n, uint8_t *zy_out, uint8_t *commitments_out,
+                                   uint8_t *proofs_out);
 /*
  * Per-stage device timing of the calls on this context, measured with CUDA events on the
  * context's stream (bench.py's roofline numbers come from here).  enable(1) resets the

@@ -486,21 +486,19 @@ extern "C" int kzg_b200_verify_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const uin
     return rc;
 }
 
-// The same for blobs, commitments and proofs that are already in this context's GPU memory (16-byte aligned).
-// Every validation and every Fiat-Shamir challenge of the call runs in ONE launch each (per chunk they are
-// latency-bound: one SHA-256 stream per blob), the evaluations chunk by chunk; 160 bytes per blob come back to
-// the host for the sequential hash of compute_r_powers, and the final pairing check runs on the host.  Synchronous.
-extern "C" int kzg_b200_verify_blob_kzg_proof_batch_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments,
-                                                           const uint8_t *d_proofs, size_t n, int *ok) {
-    if (!ctx || !ok || (n && (!d_blobs || !d_commitments || !d_proofs))) return KZG_B200_BAD_ARGS;
-    if (!aligned16(d_blobs) || !aligned16(d_commitments) || !aligned16(d_proofs)) return KZG_B200_BAD_ARGS;
-    *ok = 0;
-    if (n == 0) { *ok = 1; return KZG_B200_OK; }
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    CU(cudaSetDevice(ctx->device));
+// Phase A over blobs, commitments and proofs that are already in this context's GPU memory (16-byte aligned).
+// Every validation and every Fiat-Shamir challenge of the call runs in ONE launch each (per chunk they are latency-bound:
+// one SHA-256 stream per blob), the evaluations chunk by chunk.  On return (synchronous) the decoded points and the (z, y)
+// records are in vb, and the pinned host buffer holds zy (n x 64), the commitment and proof bytes (n x 48 each) -- what
+// compute_r_powers hashes -- and every point and field element has been checked.  hs != nullptr: that hash is computed
+// here, chunk by chunk while the GPU evaluates the next chunk.
+struct HostRecords { const uint8_t *zy, *commitments, *proofs; };
+static int verify_phase_a_device_locked(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments, const uint8_t *d_proofs,
+                                        size_t n, VerifyBufs *vb_out, HostSha256 *hs, HostRecords *rec) {
     const size_t bpb = (size_t)ctx->n * 32;
     VerifyBufs vb;
     RC(verify_bufs(ctx, n, &vb));
+    *vb_out = vb;
     if (n > ctx->z_all_elems) {
         if (ctx->d_z_all) CU(cudaFree(ctx->d_z_all));
         ctx->d_z_all = nullptr;
@@ -513,7 +511,7 @@ extern "C" int kzg_b200_verify_blob_kzg_proof_batch_device(kzg_b200_ctx *ctx, co
     CU(cudaMemsetAsync(vb.status, 0, n * sizeof(int32_t), sm));
     // Where the validation of the 2n points runs: beside the hash while both fit one warp per scheduler (up to ~4,700 blobs);
     // for larger calls beside the evaluation, after the hash -- two latency-bound kernels that share schedulers cost far more
-    // than they overlap (tools/order_ab.py: 8,192 blobs 21.1 ms beside the hash, 14.0 ms beside the evaluation).
+    // than they overlap (profiles/validate_order_r2ab.txt: 8,192 blobs 21.1 ms beside the hash, 14.0 ms beside the evaluation).
     const int order = fr_challenge_form(n, n, ctx->sms) >= 2 ? 0 : 2;
     int rc;
     auto validate = [&](cudaStream_t s_) -> int {
@@ -573,21 +571,67 @@ extern "C" int kzg_b200_verify_blob_kzg_proof_batch_device(kzg_b200_ctx *ctx, co
     }
     CU(cudaStreamWaitEvent(sm, ln->ev_side_join, 0));
     CU(cudaMemcpyAsync(h_st, vb.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, sm));
-    HostSha256 hs;
-    compute_r_begin(hs, (uint64_t)ctx->n, n);
     CU(cudaEventSynchronize(ctx->ev_chunks[nchunks]));
-    for (size_t c = 0; c < nchunks; c++) {
-        const size_t off = c * ctx->chunk, cnt = std::min(ctx->chunk, n - off);
-        CU(cudaEventSynchronize(ctx->ev_chunks[c]));
-        compute_r_update(hs, h_cm + 48 * off, h_zy + 64 * off, h_pr + 48 * off, cnt);
+    if (hs) {
+        for (size_t c = 0; c < nchunks; c++) {
+            const size_t off = c * ctx->chunk, cnt = std::min(ctx->chunk, n - off);
+            CU(cudaEventSynchronize(ctx->ev_chunks[c]));
+            compute_r_update(*hs, h_cm + 48 * off, h_zy + 64 * off, h_pr + 48 * off, cnt);
+        }
     }
     CU(cudaStreamSynchronize(sm));
+    stage_collect(ctx);
     for (size_t i = 0; i < n; i++)
         if (h_st[i] != KZG_B200_OK) return KZG_B200_BAD_ARGS;
+    rec->zy = h_zy;
+    rec->commitments = h_cm;
+    rec->proofs = h_pr;
+    return KZG_B200_OK;
+}
+
+// `verify_blob_kzg_proof_batch` over device-resident inputs: 160 bytes per blob come back to the host for the sequential
+// hash of compute_r_powers, and the final pairing check runs on the host.  Synchronous.
+extern "C" int kzg_b200_verify_blob_kzg_proof_batch_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments,
+                                                           const uint8_t *d_proofs, size_t n, int *ok) {
+    if (!ctx || !ok || (n && (!d_blobs || !d_commitments || !d_proofs))) return KZG_B200_BAD_ARGS;
+    if (!aligned16(d_blobs) || !aligned16(d_commitments) || !aligned16(d_proofs)) return KZG_B200_BAD_ARGS;
+    *ok = 0;
+    if (n == 0) { *ok = 1; return KZG_B200_OK; }
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    VerifyBufs vb;
+    HostRecords rec;
+    HostSha256 hs;
+    compute_r_begin(hs, (uint64_t)ctx->n, n);
+    RC(verify_phase_a_device_locked(ctx, d_blobs, d_commitments, d_proofs, n, &vb, &hs, &rec));
     uint8_t r[32], partial[224];
     compute_r_finish(hs, r);
     RC(verify_phase_b_device(ctx, vb, n, n, r, 0, partial));
     return host_verify_finish(partial, 1, ctx->tau_prepared, ok) == 0 ? KZG_B200_OK : KZG_B200_BAD_ARGS;
+}
+
+// Phase A of the two-phase form (kzg_b200_verify_phase_a) for a shard that is already in this context's GPU memory.
+// zy_out: n x 64 B on the host; commitments_out / proofs_out (optional, n x 48 B each, host): the shard's compressed points,
+// which the caller needs on the host anyway for the exchange and for kzg_b200_compute_r.  The decoded points stay in the
+// context: kzg_b200_verify_phase_b on the same bytes uses them as they are.
+extern "C" int kzg_b200_verify_phase_a_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments,
+                                              const uint8_t *d_proofs, size_t n, uint8_t *zy_out, uint8_t *commitments_out,
+                                              uint8_t *proofs_out) {
+    if (!ctx || (n && (!d_blobs || !d_commitments || !d_proofs || !zy_out))) return KZG_B200_BAD_ARGS;
+    if (!aligned16(d_blobs) || !aligned16(d_commitments) || !aligned16(d_proofs)) return KZG_B200_BAD_ARGS;
+    if (n == 0) return KZG_B200_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    VerifyBufs vb;
+    HostRecords rec;
+    RC(verify_phase_a_device_locked(ctx, d_blobs, d_commitments, d_proofs, n, &vb, nullptr, &rec));
+    memcpy(zy_out, rec.zy, 64 * n);
+    if (commitments_out) memcpy(commitments_out, rec.commitments, 48 * n);
+    if (proofs_out) memcpy(proofs_out, rec.proofs, 48 * n);
+    points_digest(ctx->va_digest, rec.commitments, rec.proofs, n);
+    ctx->va_n = n;
+    ctx->va_valid = true;
+    return KZG_B200_OK;
 }
 
 // reference verify_kzg_proof (src/kzg.rs:429-445 -> verify_kzg_proof_impl :409-426): no blob, the caller gives

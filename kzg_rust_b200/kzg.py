@@ -97,6 +97,7 @@ def load_library():
     L.kzg_b200_compute_blob_kzg_proof_device.argtypes = [vp, vp, vp, sz, vp, vp]
     L.kzg_b200_synchronize.argtypes = [vp]
     L.kzg_b200_verify_blob_kzg_proof_batch_device.argtypes = [vp, vp, vp, vp, sz, pci]
+    L.kzg_b200_verify_phase_a_device.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
     L.kzg_b200_stream.argtypes = [vp]
     L.kzg_b200_stream.restype = vp
     L.kzg_b200_verify_kzg_proof.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]

@@ -46,6 +46,16 @@ class CudaBackend:
                                             zy.ctypes.data)
         return rc, zy.reshape(-1)
 
+    def phase_a_device(self, d_blobs, d_commitments, d_proofs, n):
+        """The same for a shard that is already in this GPU's memory (device pointers, 16-byte aligned).  Returns
+        (rc, zy, commitments, proofs) with the compressed points copied to the host for the exchange."""
+        zy = np.zeros(64 * n, dtype=np.uint8)
+        cm = np.zeros(48 * n, dtype=np.uint8)
+        pr = np.zeros(48 * n, dtype=np.uint8)
+        rc = self.L.kzg_b200_verify_phase_a_device(self.s._h, d_blobs, d_commitments, d_proofs, n, zy.ctypes.data, cm.ctypes.data,
+                                                   pr.ctypes.data)
+        return rc, zy, cm, pr
+
     def compute_r(self, commitments, zy, proofs):
         r = np.zeros(32, dtype=np.uint8)
         rc = self.L.kzg_b200_compute_r(self.s._h, commitments.ctypes.data, zy.ctypes.data, proofs.ctypes.data,
@@ -93,17 +103,10 @@ def verify_blob_kzg_proof_batch_sharded(backend, blobs, commitments, proofs, n_t
     Two collectives per verdict: one all_gather of the shards' records (status byte + 160 B per blob: C_i, z_i,
     y_i, proof_i -- exactly what compute_r_powers hashes, so every rank derives the same r without a broadcast),
     and one all_gather of the 224-byte partial sums (+ status byte)."""
-    import time
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
-    t_last = [time.perf_counter()]
-
-    def mark(name):  # trace: a dict that receives the wall-clock milliseconds of every step on this rank
-        if trace is not None:
-            now = time.perf_counter()
-            trace[name] = trace.get(name, 0.0) + (now - t_last[0]) * 1e3
-            t_last[0] = now
+    mark = _marker(trace)
     lo, hi = shard_range(n_total, rank, world)
     n_local = hi - lo
     blobs, commitments, proofs = _u8(blobs), _u8(commitments), _u8(proofs)
@@ -113,6 +116,47 @@ def verify_blob_kzg_proof_batch_sharded(backend, blobs, commitments, proofs, n_t
         return True
     rc, zy = backend.phase_a(blobs, commitments, proofs) if n_local else (0, np.zeros(0, np.uint8))
     mark("phase_a")
+    return _exchange_and_finish(backend, rc, zy, commitments, proofs, n_total, lo, n_local, device, mark)
+
+
+def verify_blob_kzg_proof_batch_sharded_device(backend, d_blobs, d_commitments, d_proofs, n_total, device, trace=None):
+    """The same for shards that are already in each rank's GPU memory: d_* are contiguous torch uint8 CUDA tensors holding
+    this rank's shard_range(n_total, rank, world) blobs, commitments and proofs.  Phase A reads them where they are
+    (no upload); 160 bytes per blob come to the host for the exchange, as in the host form."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    mark = _marker(trace)
+    lo, hi = shard_range(n_total, rank, world)
+    n_local = hi - lo
+    if d_commitments.numel() != 48 * n_local or d_proofs.numel() != 48 * n_local:
+        raise _k.BadArgs("shard does not match shard_range(n_total, rank, world)")
+    if n_total == 0:
+        return True
+    if n_local:
+        rc, zy, commitments, proofs = backend.phase_a_device(d_blobs.data_ptr(), d_commitments.data_ptr(), d_proofs.data_ptr(), n_local)
+    else:
+        rc, zy, commitments, proofs = 0, np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(0, np.uint8)
+    mark("phase_a")
+    return _exchange_and_finish(backend, rc, zy, commitments, proofs, n_total, lo, n_local, device, mark)
+
+
+def _marker(trace):
+    import time
+    t_last = [time.perf_counter()]
+
+    def mark(name):  # trace: a dict that receives the wall-clock milliseconds of every step on this rank
+        if trace is not None:
+            now = time.perf_counter()
+            trace[name] = trace.get(name, 0.0) + (now - t_last[0]) * 1e3
+            t_last[0] = now
+    return mark
+
+
+def _exchange_and_finish(backend, rc, zy, commitments, proofs, n_total, lo, n_local, device, mark):
+    """Everything after phase A: the records' all_gather, r, phase B, the partials' all_gather, the final check."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
     if world > 1:
         counts = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
         rec = np.zeros(1 + 160 * n_local, dtype=np.uint8)

@@ -54,6 +54,7 @@ extern "C" {
     pub fn kzg_b200_compute_blob_kzg_proof_device(ctx: *mut KzgB200Ctx, d_blobs: *const u8, d_commitments: *const u8, n: usize, d_proofs_out: *mut u8, d_status: *mut i32) -> c_int;
     pub fn kzg_b200_synchronize(ctx: *mut KzgB200Ctx) -> c_int;
     pub fn kzg_b200_verify_blob_kzg_proof_batch_device(ctx: *mut KzgB200Ctx, d_blobs: *const u8, d_commitments: *const u8, d_proofs: *const u8, n: usize, ok: *mut c_int) -> c_int;
+    pub fn kzg_b200_verify_phase_a_device(ctx: *mut KzgB200Ctx, d_blobs: *const u8, d_commitments: *const u8, d_proofs: *const u8, n: usize, zy_out: *mut u8, commitments_out: *mut u8, proofs_out: *mut u8) -> c_int;
     pub fn kzg_b200_profile_enable(ctx: *mut KzgB200Ctx, on: c_int) -> c_int;
     pub fn kzg_b200_profile_read(ctx: *mut KzgB200Ctx, ms_out: *mut f64, launches_out: *mut u64) -> c_int;
     pub fn kzg_b200_stream(ctx: *mut KzgB200Ctx) -> *mut c_void;

@@ -403,3 +403,38 @@ def test_phase_b_bucket_method_equals_the_ladders(n):
         for c in (1, 2, 5, 9, 12):
             if n <= 300 or c >= 5:
                 assert partial(first, KZG_B200_PIP_C=c) == want, (n, first, c)
+
+
+def test_device_resident_phase_a_and_sharded_form():
+    """kzg_b200_verify_phase_a_device: the same (z, y) records as the host-buffer phase A, the compressed points handed
+    back for the exchange, phase B reusing what it validated; the sharded driver over device-resident shards (one rank)
+    accepts the batch and rejects a tampered one; malformed input and misaligned pointers are refused."""
+    import torch
+    from kzg_rust_b200 import sharded
+    k = _kzg()
+    L = k.load_library()
+    s = gpu_settings("mainnet", 8)
+    n = 9
+    blobs, cms, proofs = _make_batch(k, s, n, 1234)
+    dev = torch.device("cuda", 0)
+    d_b, d_c, d_p = (torch.from_numpy(a.copy()).to(dev) for a in (blobs, cms, proofs))
+    zy_h = np.zeros((n, 64), dtype=np.uint8)
+    assert L.kzg_b200_verify_phase_a(s._h, blobs.ctypes.data, cms.ctypes.data, proofs.ctypes.data, n, zy_h.ctypes.data) == 0
+    be = sharded.CudaBackend(s)
+    rc, zy, cm, pr = be.phase_a_device(d_b.data_ptr(), d_c.data_ptr(), d_p.data_ptr(), n)
+    assert rc == 0 and zy.tobytes() == zy_h.tobytes() and cm.tobytes() == cms.tobytes() and pr.tobytes() == proofs.tobytes()
+    r = be.compute_r(cm, zy, pr)
+    rc, part = be.phase_b(cm, zy, pr, r, 0)
+    assert rc == 0 and be.finish(part) is True
+    assert sharded.verify_blob_kzg_proof_batch_sharded_device(be, d_b, d_c, d_p, n, dev) is True
+    bad = d_p.clone()
+    bad[[0, n - 1]] = bad[[n - 1, 0]]
+    assert sharded.verify_blob_kzg_proof_batch_sharded_device(be, d_b, d_c, bad, n, dev) is False
+    # a commitment that is not a point, a non-canonical blob element, a misaligned pointer
+    broken = d_c.clone()
+    broken[3, 5] ^= 0x55
+    assert be.phase_a_device(d_b.data_ptr(), broken.data_ptr(), d_p.data_ptr(), n)[0] == 1
+    nb = d_b.clone()
+    nb[2, :32] = 0xff
+    assert be.phase_a_device(nb.data_ptr(), d_c.data_ptr(), d_p.data_ptr(), n)[0] == 1
+    assert be.phase_a_device(d_b.data_ptr() + 4, d_c.data_ptr(), d_p.data_ptr(), n - 1)[0] == 1
