@@ -11,9 +11,11 @@ using namespace kzg;
 int fr_setup_roots_device(int n, fr_t **d_roots, cudaStream_t stream) { return fr_setup_roots(n, d_roots, stream); }
 
 template <int G>
-static void launch_challenge_group(cudaStream_t st, const uint8_t *d_blobs, const uint8_t *d_commitments, size_t count, int n, fr_t *d_z) {
+static void launch_challenge_group(cudaStream_t st, const uint8_t *d_blobs, const uint8_t *d_commitments, size_t count, int n, fr_t *d_z,
+                                   uint32_t blk_begin = 0, uint32_t blk_end = 0xffffffffu, uint32_t *d_state = nullptr) {
     const size_t warps = (count * G + 31) / 32;
-    k_challenge_group<G><<<blocks_for(warps, 4), 128, 0, st>>>(d_blobs, d_commitments, (uint32_t)count, n, d_z, 1u);
+    k_challenge_group<G><<<blocks_for(warps, 4), 128, 0, st>>>(d_blobs, d_commitments, (uint32_t)count, n, d_z, 1u, blk_begin, blk_end,
+                                                               reinterpret_cast<uint4 *>(d_state));
 }
 // The most lanes per blob that still leave every warp of the launch a scheduler of its own (frpath.cuh).  The validation of
 // the chunk's points (`beside` blocks of four warps, one thread per point) runs beside the hash and is just as latency-bound:
@@ -45,6 +47,23 @@ int fr_launch_challenge(cudaStream_t st, const uint8_t *d_blobs, const uint8_t *
         case 4: launch_challenge_group<4>(st, d_blobs, d_commitments, count, n, d_z); break;
         case 2: launch_challenge_group<2>(st, d_blobs, d_commitments, count, n, d_z); break;
         default: k_challenge<<<blocks_for(count, 64), 64, 0, st>>>(d_blobs, d_commitments, (uint32_t)count, n, d_z);
+    }
+    CU(cudaGetLastError());
+    return KZG_B200_OK;
+}
+// Blocks [blk_begin, blk_end) of the message only (grouped forms: g lanes per blob, g >= 2 as fr_challenge_form returned it;
+// blk_begin a multiple of 32).  d_state: count x 8 words, the running state between the launches of one hash.
+int fr_launch_challenge_range(cudaStream_t st, const uint8_t *d_blobs, const uint8_t *d_commitments, size_t count, int n, fr_t *d_z,
+                              int g, uint32_t blk_begin, uint32_t blk_end, uint32_t *d_state) {
+    if (count == 0) return KZG_B200_OK;
+    if (!d_state || (blk_begin & 31u) || blk_begin >= blk_end) return KZG_B200_BAD_ARGS;
+    switch (g) {
+        case 32: launch_challenge_group<32>(st, d_blobs, d_commitments, count, n, d_z, blk_begin, blk_end, d_state); break;
+        case 16: launch_challenge_group<16>(st, d_blobs, d_commitments, count, n, d_z, blk_begin, blk_end, d_state); break;
+        case 8: launch_challenge_group<8>(st, d_blobs, d_commitments, count, n, d_z, blk_begin, blk_end, d_state); break;
+        case 4: launch_challenge_group<4>(st, d_blobs, d_commitments, count, n, d_z, blk_begin, blk_end, d_state); break;
+        case 2: launch_challenge_group<2>(st, d_blobs, d_commitments, count, n, d_z, blk_begin, blk_end, d_state); break;
+        default: return KZG_B200_BAD_ARGS;
     }
     CU(cudaGetLastError());
     return KZG_B200_OK;

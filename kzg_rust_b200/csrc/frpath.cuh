@@ -157,9 +157,14 @@ KZG_D uint32_t challenge_msg_word(const uint8_t *__restrict__ blob, const uint8_
     return 0u;
 }
 // one block of four warps; kw: 4 x 64 x 32 words of shared memory
+// blk_begin / blk_end: the 64-byte blocks of the message this launch hashes (multiples of 32 blocks, or the end of the message).
+// A launch that does not start at block 0 takes the running state of blob b from state[b], one that does not reach the end
+// leaves it there: the hash of a chunk whose blobs are still being uploaded runs slice by slice behind the copies
+// (verify_chunk_a, proof_verify.inl).
 template <int G>
 KZG_D void challenge_group_block(uint32_t (*kw)[64 * 32], uint32_t block, const uint8_t *__restrict__ blobs,
-                                 const uint8_t *__restrict__ commitments, uint32_t count, int n, fr_t *__restrict__ z_out, uint32_t one) {
+                                 const uint8_t *__restrict__ commitments, uint32_t count, int n, fr_t *__restrict__ z_out, uint32_t one,
+                                 uint32_t blk_begin, uint32_t blk_end, uint4 *__restrict__ state) {
     constexpr uint32_t K[64] = {KZG_SHA256_K};
     auto fadd = [one](uint32_t x, uint32_t y) -> uint32_t { return sha_fadd(x, y, one); };  // an IMAD (FMA pipe), see sha256.cuh
     constexpr uint32_t PER_WARP = 32 / G;
@@ -172,12 +177,18 @@ KZG_D void challenge_group_block(uint32_t (*kw)[64 * 32], uint32_t block, const 
     const uint8_t *cm = commitments + (size_t)b * 48;
     const uint32_t msg_end = 32u + 32u * (uint32_t)n + 48u, nblocks = (msg_end + 9u + 63u) / 64u;
     uint32_t h[8];
-    sha256_init(h);
+    blk_end = min(blk_end, nblocks);
+    if (blk_begin == 0) {
+        sha256_init(h);
+    } else {
+        const uint4 lo = state[2 * b], hi = state[2 * b + 1];
+        h[0] = lo.x; h[1] = lo.y; h[2] = lo.z; h[3] = lo.w; h[4] = hi.x; h[5] = hi.y; h[6] = hi.z; h[7] = hi.w;
+    }
     uint32_t *mine = kw[warp];
 #pragma unroll 1
-    for (uint32_t base = 0; base < nblocks; base += G) {
+    for (uint32_t base = blk_begin; base < blk_end; base += G) {
         const uint32_t blk = base + sub;
-        if (blk < nblocks) {
+        if (blk < blk_end) {
             uint32_t w[16];
             if (blk >= 1 && 64u * blk + 64u <= 32u + 32u * (uint32_t)n) {  // both halves inside the blob: 128-bit loads
                 ld_be_words8(w, blob + 64 * (size_t)blk - 32);
@@ -202,7 +213,7 @@ KZG_D void challenge_group_block(uint32_t (*kw)[64 * 32], uint32_t block, const 
             }
         }
         __syncwarp();
-        const uint32_t nb = min((uint32_t)G, nblocks - base);
+        const uint32_t nb = min((uint32_t)G, blk_end - base);
 #pragma unroll 1
         for (uint32_t i = 0; i < nb; i++) {
             const uint32_t col = slot * G + i;
@@ -228,6 +239,11 @@ KZG_D void challenge_group_block(uint32_t (*kw)[64 * 32], uint32_t block, const 
         __syncwarp();
     }
     if (sub == 0 && live) {
+        if (blk_end < nblocks) {
+            state[2 * b] = make_uint4(h[0], h[1], h[2], h[3]);
+            state[2 * b + 1] = make_uint4(h[4], h[5], h[6], h[7]);
+            return;
+        }
         fr_t z;
 #pragma unroll
         for (int i = 0; i < 8; i++) z.l[i] = h[7 - i];
@@ -237,9 +253,10 @@ KZG_D void challenge_group_block(uint32_t (*kw)[64 * 32], uint32_t block, const 
 }
 template <int G>
 __global__ void __launch_bounds__(128) k_challenge_group(const uint8_t *__restrict__ blobs, const uint8_t *__restrict__ commitments,
-                                                         uint32_t count, int n, fr_t *__restrict__ z_out, uint32_t one) {
+                                                         uint32_t count, int n, fr_t *__restrict__ z_out, uint32_t one,
+                                                         uint32_t blk_begin, uint32_t blk_end, uint4 *__restrict__ state) {
     __shared__ uint32_t kw[4][64 * 32];  // [round t][lane]: conflict-free writes; reads are broadcasts inside a blob's lanes
-    challenge_group_block<G>(kw, blockIdx.x, blobs, commitments, count, n, z_out, one);
+    challenge_group_block<G>(kw, blockIdx.x, blobs, commitments, count, n, z_out, one, blk_begin, blk_end, state);
 }
 // caller-supplied evaluation points (compute_kzg_proof): 32 big-endian bytes each, must be
 // canonical (reference src/kzg.rs:452 -> bytes_to_bls_field)

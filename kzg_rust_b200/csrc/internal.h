@@ -46,6 +46,7 @@ struct DeviceBuf {
 };
 
 #define KZG_SLOTS 3
+#define KZG_HASH_SLICES 8
 struct kzg_b200_ctx {
     int device = 0;
     int n = 0;            // FIELD_ELEMENTS_PER_BLOB
@@ -77,6 +78,7 @@ struct kzg_b200_ctx {
         kzg::fr_t *d_poly = nullptr;       // chunk x n evaluations (proof / verify paths)
         kzg::fr_t *d_inv = nullptr;        // chunk x n prefix products, then 1/(z - w_i), then the quotient
         kzg::fr_t *d_z = nullptr;          // chunk challenges / evaluation points (canonical)
+        uint32_t *d_sha_state = nullptr;   // chunk x 8 words: SHA-256 states between the slice launches of a chunk's hash
         uint8_t *d_zy = nullptr;           // chunk x 64 B: z || y big-endian
         kzg::g1_affine_t *d_pts = nullptr; // chunk x 2 decoded commitments / proofs
         cudaEvent_t ev_done = nullptr;
@@ -101,6 +103,13 @@ struct kzg_b200_ctx {
     cudaEvent_t ev_aux[KZG_SLOTS] = {nullptr, nullptr, nullptr};
     bool aux_recorded[KZG_SLOTS] = {false, false, false};
     cudaEvent_t aux_ready = nullptr;  // ev_aux of the chunk being enqueued, when its upload recorded one
+    // Host verification uploads the blobs of a chunk in KZG_HASH_SLICES column slices (slice k = bytes [k W, (k+1) W) of EVERY
+    // blob of the chunk, one 2-D copy), each behind its own event: a blob's SHA-256 is sequential over its bytes, so the hash
+    // of slice k runs while slice k+1 is on the wire and ends one slice after the upload instead of one whole hash after it.
+    cudaEvent_t ev_slice[KZG_SLOTS][KZG_HASH_SLICES] = {};
+    int slices_recorded[KZG_SLOTS] = {0, 0, 0};  // slices the upload of the slot was cut into (0: one plain copy)
+    int cur_slices = 0;                          // of the chunk being enqueued
+    cudaEvent_t *cur_slice_ev = nullptr;
     host_g2_prepared *tau_prepared = nullptr;  // Miller-loop lines of [tau]G2
     kzg::g1_affine_t *d_sums_all = nullptr; // sums of a whole device-resident call, [bit position][blob] (grow-only)
     size_t sums_all_elems = 0;
@@ -173,6 +182,9 @@ int fr_challenge_form(size_t count, size_t call_blobs, int sms);
 // call_blobs: blobs of the whole call this launch is a chunk of (picks the form of the hash kernel)
 int fr_launch_challenge(cudaStream_t st, const uint8_t *d_blobs, const uint8_t *d_commitments, size_t count, int n, kzg::fr_t *d_z,
                         size_t call_blobs, int sms);
+// blocks [blk_begin, blk_end) of the hash only, state carried in d_state (count x 8 words); g = fr_challenge_form(..) >= 2
+int fr_launch_challenge_range(cudaStream_t st, const uint8_t *d_blobs, const uint8_t *d_commitments, size_t count, int n, kzg::fr_t *d_z,
+                              int g, uint32_t blk_begin, uint32_t blk_end, uint32_t *d_state);
 int fr_launch_load_scalars(cudaStream_t st, const uint8_t *d_in, size_t count, kzg::fr_t *d_out, int32_t *d_status);
 // y_i = p_i(z_i) (+ the quotient (p_i(X) - y_i)/(X - z_i) as canonical scalars in d_inv when quotient != 0)
 int fr_launch_eval(cudaStream_t st, int quotient, const uint8_t *d_blobs, const kzg::fr_t *d_z, const kzg::fr_t *d_roots, int n,

@@ -58,8 +58,9 @@ static size_t scratch_bytes(const kzg_b200_ctx *ctx) {
 static void free_workspace(kzg_b200_ctx *ctx) {
     for (auto &ln : ctx->lanes) {
         msm_free_lane(ln);
-        cudaFree(ln.d_poly); cudaFree(ln.d_inv); cudaFree(ln.d_z); cudaFree(ln.d_zy); cudaFree(ln.d_pts);
+        cudaFree(ln.d_poly); cudaFree(ln.d_inv); cudaFree(ln.d_z); cudaFree(ln.d_zy); cudaFree(ln.d_pts); cudaFree(ln.d_sha_state);
         ln.d_poly = ln.d_inv = ln.d_z = nullptr;
+        ln.d_sha_state = nullptr;
         ln.d_zy = nullptr;
         ln.d_pts = nullptr;
     }
@@ -76,6 +77,7 @@ static int alloc_workspace(kzg_b200_ctx *ctx, size_t chunk) {
         CU(cudaMalloc(&ln.d_poly, chunk * (size_t)ctx->n * sizeof(fr_t)));
         CU(cudaMalloc(&ln.d_inv, chunk * (size_t)ctx->n * sizeof(fr_t)));
         CU(cudaMalloc(&ln.d_z, chunk * sizeof(fr_t)));
+        CU(cudaMalloc(&ln.d_sha_state, chunk * 8 * sizeof(uint32_t)));
         CU(cudaMalloc(&ln.d_zy, chunk * 64));
         CU(cudaMalloc(&ln.d_pts, chunk * 2 * sizeof(g1_affine_t)));
     }
@@ -141,6 +143,7 @@ static int ctx_init(kzg_b200_ctx *ctx, const uint8_t *g1_lagrange, size_t n1, co
         CU(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_aux[i], cudaEventDisableTiming));
+        for (int k = 0; k < KZG_HASH_SLICES; k++) CU(cudaEventCreateWithFlags(&ctx->ev_slice[i][k], cudaEventDisableTiming));
     }
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
@@ -268,6 +271,8 @@ extern "C" void kzg_b200_ctx_destroy(kzg_b200_ctx *ctx) {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
         if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
         if (ctx->ev_aux[i]) cudaEventDestroy(ctx->ev_aux[i]);
+        for (int k = 0; k < KZG_HASH_SLICES; k++)
+            if (ctx->ev_slice[i][k]) cudaEventDestroy(ctx->ev_slice[i][k]);
     }
     stage_collect(ctx);
     host_g2_prepared_free(ctx->tau_prepared);
@@ -423,6 +428,7 @@ static int staged_chunks(kzg_b200_ctx *ctx, size_t n, size_t piece, Upload uploa
         size_t off = i * piece, cnt = std::min(piece, n - off);
         CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[slot], 0));  // the chunk that used this slot is done
         ctx->aux_recorded[slot] = false;
+        ctx->slices_recorded[slot] = 0;
         RC(upload(slot, off, cnt));
         CU(cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_stream));
         return KZG_B200_OK;
@@ -437,10 +443,14 @@ static int staged_chunks(kzg_b200_ctx *ctx, size_t n, size_t piece, Upload uploa
         size_t off = i * piece, cnt = std::min(piece, n - off);
         if (i + ahead < nchunks) RC(enqueue_upload(i + ahead));
         lane_select(ctx, i);
-        CU(cudaStreamWaitEvent(ctx->cur->stream, ctx->ev_h2d[slot], 0));
+        // a sliced upload is waited for slice by slice by the chunk itself (verify_chunk_a); its last slice event is ev_h2d's equal
+        ctx->cur_slices = ctx->slices_recorded[slot];
+        ctx->cur_slice_ev = ctx->ev_slice[slot];
+        if (!ctx->cur_slices) CU(cudaStreamWaitEvent(ctx->cur->stream, ctx->ev_h2d[slot], 0));
         ctx->aux_ready = ctx->aux_recorded[slot] ? ctx->ev_aux[slot] : nullptr;
         int run_rc = run(slot, off, cnt);
         ctx->aux_ready = nullptr;
+        ctx->cur_slices = 0;
         RC(run_rc);
         CU(cudaEventRecord(ctx->ev_free[slot], ctx->cur->stream));
     }

@@ -254,8 +254,23 @@ static int verify_chunk_a(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8
     RC(rc);
     if (side) CU(cudaEventRecord(ln->ev_side_join, sd));
     stage_begin(ctx, KZG_B200_STAGE_CHALLENGE);
-    rc = fr_launch_challenge(sm, d_blobs, d_commitments, cnt, ctx->n, ln->d_z, ctx->call_blobs, ctx->sms);
-    stage_end(ctx, 1);
+    if (ctx->cur_slices > 1) {
+        // the blobs arrive in column slices: slice k holds message blocks [k B, (k+1) B) of every blob (the 32-byte header shifts
+        // the blocks by half a block, so the block that straddles two slices goes with the later one), the last slice runs to the
+        // end of the message (commitment + padding).  Each launch waits for its slice only.
+        const int S = ctx->cur_slices, g = fr_challenge_form(cnt, ctx->call_blobs, ctx->sms);
+        const uint32_t per = (uint32_t)((size_t)ctx->n * 32 / S / 64);
+        for (int k = 0; k < S && rc == KZG_B200_OK; k++) {
+            CU(cudaStreamWaitEvent(sm, ctx->cur_slice_ev[k], 0));
+            rc = fr_launch_challenge_range(sm, d_blobs, d_commitments, cnt, ctx->n, ln->d_z, g, k * per, k == S - 1 ? 0xffffffffu : (k + 1) * per,
+                                           ln->d_sha_state);
+        }
+        stage_end(ctx, S);
+        ctx->launches += S - 1;
+    } else {
+        rc = fr_launch_challenge(sm, d_blobs, d_commitments, cnt, ctx->n, ln->d_z, ctx->call_blobs, ctx->sms);
+        stage_end(ctx, 1);
+    }
     RC(rc);
     stage_begin(ctx, KZG_B200_STAGE_EVAL);
     rc = fr_launch_eval(sm, 0, d_blobs, ln->d_z, ctx->d_roots, ctx->n, ln->d_inv, ln->d_poly, vb.zy + 64 * off, d_st, cnt);
@@ -282,6 +297,9 @@ static int verify_phase_a_locked(kzg_b200_ctx *ctx, const uint8_t *blobs, const 
     RC(ensure_pinned(ctx, n * (64 + sizeof(int32_t))));
     uint8_t *h_zy = ctx->h_pin;
     int32_t *h_st = reinterpret_cast<int32_t *>(ctx->h_pin + 64 * n);
+    // KZG_B200_HASH_SLICES (1 = plain copies), KZG_B200_SLICE_MIN_BLOBS: smallest chunk that is uploaded in slices
+    const int slices = std::min(KZG_HASH_SLICES, std::max(1, env_int("KZG_B200_HASH_SLICES", KZG_HASH_SLICES)));
+    const int slice_min = std::max(1, env_int("KZG_B200_SLICE_MIN_BLOBS", 64));
     RC(staged_chunks(
         ctx, n, (size_t)std::max(1, env_int("KZG_B200_VERIFY_PIECE", KZG_VERIFY_PIECE)),
         [&](int slot, size_t off, size_t cnt) -> int {
@@ -290,7 +308,22 @@ static int verify_phase_a_locked(kzg_b200_ctx *ctx, const uint8_t *blobs, const 
             CU(cudaMemcpyAsync(aux + cnt * 48, proofs + off * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->copy_stream));
             CU(cudaEventRecord(ctx->ev_aux[slot], ctx->copy_stream));
             ctx->aux_recorded[slot] = true;
-            CU(cudaMemcpyAsync(ctx->d_stage_in + slot * ch * bpb, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->copy_stream));
+            uint8_t *d_blobs = ctx->d_stage_in + slot * ch * bpb;
+            // Column slices (see internal.h): worth it when the hash has lanes to spare (a grouped form) and a slice still is a
+            // long row per blob; the hash of a slice must be a whole number of 32-block groups.
+            const int S = slices;
+            const bool sliced = S > 1 && !ctx->profile && cnt >= (size_t)slice_min && bpb % ((size_t)S * 64 * 32) == 0 &&
+                                fr_challenge_form(cnt, n, ctx->sms) >= 2;
+            if (!sliced) {
+                CU(cudaMemcpyAsync(d_blobs, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->copy_stream));
+                return KZG_B200_OK;
+            }
+            const size_t w = bpb / S;
+            for (int k = 0; k < S; k++) {
+                CU(cudaMemcpy2DAsync(d_blobs + k * w, bpb, blobs + off * bpb + k * w, bpb, w, cnt, cudaMemcpyHostToDevice, ctx->copy_stream));
+                CU(cudaEventRecord(ctx->ev_slice[slot][k], ctx->copy_stream));
+            }
+            ctx->slices_recorded[slot] = S;
             return KZG_B200_OK;
         },
         [&](int slot, size_t off, size_t cnt) -> int {

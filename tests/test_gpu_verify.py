@@ -147,6 +147,62 @@ def test_challenge_and_evaluation_match_oracle(lanes_per_blob):
         assert zy[i, 32:].tobytes() == o.evaluate_polynomial(blobs[i].tobytes(), z)
 
 
+@pytest.mark.parametrize("slices", [8, 4, 2])
+@pytest.mark.parametrize("lanes_per_blob", [0, 32, 8, 2])
+def test_sliced_upload_hash_matches_oracle(lanes_per_blob, slices):
+    """Host verification uploads a chunk's blobs in column slices and hashes slice k while slice k+1 is on the wire
+    (csrc/proof_verify.inl: verify_chunk_a): z_i, y_i stay bit-exact with the oracle for every slice count and hash form."""
+    k = _kzg()
+    L = k.load_library()
+    s = gpu_settings("mainnet", 8)
+    o = oracle_settings("mainnet")
+    blobs, cms, proofs = _make_batch(k, s, 5, 55)
+    zy = np.zeros((5, 64), dtype=np.uint8)
+    env = {"KZG_B200_SLICE_MIN_BLOBS": "1", "KZG_B200_HASH_SLICES": str(slices)}
+    if lanes_per_blob:
+        env["KZG_B200_CHALLENGE_G"] = str(lanes_per_blob)
+    os.environ.update(env)
+    try:
+        assert L.kzg_b200_verify_phase_a(s._h, blobs.ctypes.data, cms.ctypes.data, proofs.ctypes.data, 5, zy.ctypes.data) == 0
+        assert k.Kzg.verify_blob_kzg_proof_batch_raw(blobs, cms, proofs, 5, s) is True
+    finally:
+        for key in env:
+            os.environ.pop(key, None)
+    for i in range(5):
+        z = o.compute_challenge(blobs[i].tobytes(), cms[i].tobytes())
+        assert zy[i, :32].tobytes() == z
+        assert zy[i, 32:].tobytes() == o.evaluate_polynomial(blobs[i].tobytes(), z)
+
+
+def test_sliced_and_plain_uploads_agree_over_several_pieces():
+    """300 blobs in pieces of 128 (two lanes, three upload slots, a short last piece): the (z, y) records of the sliced
+    uploads equal those of plain copies, and the verdicts (true / one proof swapped / one blob byte flipped) too."""
+    k = _kzg()
+    L = k.load_library()
+    s = gpu_settings("mainnet", 8)
+    n = 300
+    blobs, cms, proofs = _make_batch(k, s, n, 3001)
+    out = {}
+    for slices in (1, 8):
+        env = {"KZG_B200_SLICE_MIN_BLOBS": "1", "KZG_B200_HASH_SLICES": str(slices), "KZG_B200_VERIFY_PIECE": "128"}
+        os.environ.update(env)
+        try:
+            zy = np.zeros((n, 64), dtype=np.uint8)
+            assert L.kzg_b200_verify_phase_a(s._h, blobs.ctypes.data, cms.ctypes.data, proofs.ctypes.data, n, zy.ctypes.data) == 0
+            bad = proofs.copy()
+            bad[[17, 290]] = bad[[290, 17]]
+            b2 = blobs.copy()
+            b2[299, 131071] ^= 1
+            out[slices] = (zy.tobytes(), k.Kzg.verify_blob_kzg_proof_batch_raw(blobs, cms, proofs, n, s),
+                           k.Kzg.verify_blob_kzg_proof_batch_raw(blobs, cms, bad, n, s),
+                           k.Kzg.verify_blob_kzg_proof_batch_raw(b2, cms, proofs, n, s))
+        finally:
+            for key in env:
+                os.environ.pop(key, None)
+    assert out[1] == out[8]
+    assert out[8][1:] == (True, False, False)
+
+
 def test_pairing_check_matches_oracle():
     from oracle import binding as ob
     k = _kzg()
