@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(64) k_horner_compress(const g1_affine_t *sums,
 // The same with one WARP per blob, for small batches where the pass is pure latency (254 dependent doublings and
 // additions per blob, 4.5 ms): lane k folds the sums 8k .. 8k + 7, then five rounds join the 32 partial results,
 // T_k + 2^(8 s) T_(k + s) -- the doublings stay on the critical path (255 of them), the additions leave it (12
-// instead of 254).  2.0 ms per call.
+// instead of 254), and from the second round on three lanes share every doubling.
 #define KZG_HORNER_WARP_MAX 1024
 __global__ void __launch_bounds__(128) k_horner_compress_warp(const g1_affine_t *sums, size_t stride, int W, const int32_t *status,
                                                               uint8_t *out, uint32_t count) {
@@ -106,13 +106,27 @@ __global__ void __launch_bounds__(128) k_horner_compress_warp(const g1_affine_t 
     __syncwarp();
 #pragma unroll 1
     for (uint32_t s = 1; s < 32; s <<= 1) {
-        if ((lane & (2 * s - 1)) == 0) {
-            g1_jac_t t = part[warp][lane + s];
+        const uint32_t role = lane & (2 * s - 1);
+        if (s == 1) {
+            if (role == 0) {
+                g1_jac_t t = part[warp][lane + s];
 #pragma unroll 1
-            for (uint32_t d = 0; d < 8 * s; d++) g1j_dbl(t, t);
-            g1_jac_t a = part[warp][lane];
-            g1j_add(t, t, a);
-            part[warp][lane] = t;
+                for (uint32_t d = 0; d < 8 * s; d++) g1j_dbl(t, t);
+                g1_jac_t a = part[warp][lane];
+                g1j_add(t, t, a);
+                part[warp][lane] = t;
+            }
+        } else if (role < 3) {
+            // from the second round on the joining lanes are at least four apart: the two lanes after each of them share
+            // its 8 s doublings (g1j_dbl_n_coop3, g1.cuh) -- 240 of the 248 doublings of the critical path
+            const uint32_t mask = s == 2 ? 0x77777777u : s == 4 ? 0x07070707u : s == 8 ? 0x00070007u : 0x00000007u;
+            g1_jac_t t = part[warp][(lane - role) + s];
+            g1j_dbl_n_coop3(t, 8 * s, mask, (int)(lane - role), (int)role);
+            if (role == 0) {
+                g1_jac_t a = part[warp][lane];
+                g1j_add(t, t, a);
+                part[warp][lane] = t;
+            }
         }
         __syncwarp();
     }

@@ -266,10 +266,11 @@ __global__ void __launch_bounds__(KZG_PIP_ROW_THREADS) k_pip_rows(PipPlan pl, co
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    // the weight 2^p: up to 128 dependent doublings, by three lanes (g1j_dbl_n_coop3, g1.cuh)
+    if (threadIdx.x < 3) {
         g1_jac_t s = red[0];
-        pip_weight(s, p);
-        rows[blockIdx.x] = s;
+        g1j_dbl_n_coop3(s, p, 0x7u, 0, (int)threadIdx.x);
+        if (threadIdx.x == 0) rows[blockIdx.x] = s;
     }
 }
 #endif  // __CUDACC__
