@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(64) k_horner_compress(const g1_affine_t *sums,
 // T_k + 2^(8 s) T_(k + s) -- the doublings stay on the critical path (255 of them), the additions leave it (12
 // instead of 254), and from the second round on three lanes share every doubling.
 #define KZG_HORNER_WARP_MAX 1024
-__global__ void __launch_bounds__(128) k_horner_compress_warp(const g1_affine_t *sums, size_t stride, int W, const int32_t *status,
+// JAC: the sums are Jacobian points (the small-batch form of the MSM, msm_run_small), canonical.
+template <bool JAC>
+__global__ void __launch_bounds__(128) k_horner_compress_warp(const void *sums_v, size_t stride, int W, const int32_t *status,
                                                               uint8_t *out, uint32_t count) {
     __shared__ g1_jac_t part[4][32];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,8 +101,13 @@ __global__ void __launch_bounds__(128) k_horner_compress_warp(const g1_affine_t 
 #pragma unroll 1
     for (int j = hi - 1; j >= lo; j--) {
         g1j_dbl(acc, acc);
-        g1_affine_t sj = horner_load(sums + (size_t)j * stride + i);
-        if (!g1a_is_inf(sj)) g1j_add_affine(acc, acc, sj.x, sj.y);
+        if (JAC) {
+            const g1_jac_t sj = static_cast<const g1_jac_t *>(sums_v)[(size_t)j * stride + i];
+            g1j_add(acc, acc, sj);
+        } else {
+            g1_affine_t sj = horner_load(static_cast<const g1_affine_t *>(sums_v) + (size_t)j * stride + i);
+            if (!g1a_is_inf(sj)) g1j_add_affine(acc, acc, sj.x, sj.y);
+        }
     }
     part[warp][lane] = acc;
     __syncwarp();
@@ -144,9 +151,18 @@ int g1_launch_horner_compress(cudaStream_t st, const g1_affine_t *d_sums, size_t
                               uint8_t *d_out, size_t count) {
     if (count == 0) return KZG_B200_OK;
     if (count <= KZG_HORNER_WARP_MAX && W <= 256)
-        k_horner_compress_warp<<<blocks_for(count, 4), 128, 0, st>>>(d_sums, stride, W, d_status, d_out, (uint32_t)count);
+        k_horner_compress_warp<false><<<blocks_for(count, 4), 128, 0, st>>>(d_sums, stride, W, d_status, d_out, (uint32_t)count);
     else
         k_horner_compress<<<blocks_for(count, 64), 64, 0, st>>>(d_sums, stride, W, d_status, d_out, (uint32_t)count);
+    CU(cudaGetLastError());
+    return KZG_B200_OK;
+}
+
+int g1_launch_horner_compress_jac(cudaStream_t st, const g1_jac_t *d_sums, size_t stride, int W, const int32_t *d_status,
+                                  uint8_t *d_out, size_t count) {
+    if (count == 0) return KZG_B200_OK;
+    if (count > KZG_HORNER_WARP_MAX || W > 256) return KZG_B200_BAD_ARGS;
+    k_horner_compress_warp<true><<<blocks_for(count, 4), 128, 0, st>>>(d_sums, stride, W, d_status, d_out, (uint32_t)count);
     CU(cudaGetLastError());
     return KZG_B200_OK;
 }

@@ -152,6 +152,14 @@ int msm_digits_from_blobs(kzg_b200_ctx *ctx, const uint8_t *d_blobs, size_t coun
 int msm_digits_from_scalars(kzg_b200_ctx *ctx, const kzg::fr_t *d_scalars, size_t count);
 // the 255 sums S_j of `count` blobs from the digits of the current lane: (*out)[j*count + b] (lazy residues)
 int msm_run(kzg_b200_ctx *ctx, size_t count, const kzg::g1_affine_t **out);
+// the same sums for a small batch, one warp per sum, as Jacobian points (no inversions on the way): see k_comb_rows_warp
+// default threshold: above ~16 blobs the sums no longer fit one wave of warps (255 per blob, eight resident per SM) and the
+// batched affine levels win (64 blobs: 2.97 ms against 1.79 ms; 1 blob: 0.16 against 0.85 ms); KZG_B200_MSM_SMALL_MAX moves
+// it up to the cap
+#define KZG_MSM_SMALL_MAX 16
+#define KZG_MSM_SMALL_CAP 64
+int msm_run_small(kzg_b200_ctx *ctx, size_t count, const kzg::g1_jac_t **out);
+bool msm_small_fits(const kzg_b200_ctx *ctx, size_t count);
 // bytes of lane workspace the MSM needs per blob of a chunk
 size_t msm_workspace_per_blob(const kzg_b200_ctx *ctx);
 int msm_alloc_lane(kzg_b200_ctx *ctx, kzg_b200_ctx::Lane &ln, size_t chunk);
@@ -169,6 +177,9 @@ int g1_launch_subgroup2(cudaStream_t st, const kzg::g1_affine_t *d_cpts, const k
 // sums[j*stride + i], j < W  ->  48-byte compressed sum_j 2^j sums[j] of blob i (zeros where status[i] != 0)
 int g1_launch_horner_compress(cudaStream_t st, const kzg::g1_affine_t *d_sums, size_t stride, int W, const int32_t *d_status,
                               uint8_t *d_out, size_t count);
+// the same from Jacobian sums (msm_run_small), small batches
+int g1_launch_horner_compress_jac(cudaStream_t st, const kzg::g1_jac_t *d_sums, size_t stride, int W, const int32_t *d_status,
+                                  uint8_t *d_out, size_t count);
 int g1_measure_peaks(kzg_b200_ctx *ctx, double *imad_per_s, double *imad_wide_per_s, double *fp_mul_per_s);
 int g1_debug_field_op(kzg_b200_ctx *ctx, int op, const uint32_t *a, const uint32_t *b, uint32_t *out, uint64_t count);
 // C_i == [p_i(tau)] G1 for every i (test aid, see kzg_b200_debug_check_tau_identity)

@@ -370,14 +370,34 @@ static int deferred_finish(kzg_b200_ctx *ctx, const DeferredCompress *dc, const 
     return rc;
 }
 
+// The MSM of one chunk from the digits of the current lane, down to the compressed points (or the parked sums).
+// Small single-chunk calls take the one-warp-per-sum form (msm_run_small; KZG_B200_MSM_SMALL_MAX blobs, 0 = never).
+static int msm_and_compress(kzg_b200_ctx *ctx, size_t off, size_t count, const int32_t *d_status, uint8_t *d_out,
+                            const DeferredCompress *dc, cudaEvent_t join = nullptr) {
+    cudaStream_t st = ctx->cur->stream;
+    const size_t small_max = (size_t)std::max(0, std::min(KZG_MSM_SMALL_CAP, env_int("KZG_B200_MSM_SMALL_MAX", KZG_MSM_SMALL_MAX)));
+    if (count <= small_max && !(dc && dc->sums) && msm_small_fits(ctx, count)) {
+        const g1_jac_t *sums = nullptr;
+        RC(msm_run_small(ctx, count, &sums));
+        if (join) CU(cudaStreamWaitEvent(st, join, 0));
+        stage_begin(ctx, KZG_B200_STAGE_COMPRESS);
+        int rc = g1_launch_horner_compress_jac(st, sums, count, ctx->W, d_status, d_out, count);
+        stage_end(ctx, 1);
+        ctx->launches++;
+        return rc;
+    }
+    const g1_affine_t *res = nullptr;
+    RC(msm_run(ctx, count, &res));
+    if (join) CU(cudaStreamWaitEvent(st, join, 0));
+    return compress_or_park(ctx, res, off, count, d_status, d_out, dc);
+}
+
 // d_out / d_status point at this chunk's slice; `off` is its first blob within the call (deferred compression)
 static int commit_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, size_t count, uint8_t *d_out, int32_t *d_status,
                         size_t off = 0, const DeferredCompress *dc = nullptr) {
     CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), ctx->cur->stream));
     RC(msm_digits_from_blobs(ctx, d_blobs, count, d_status));
-    const g1_affine_t *res = nullptr;
-    RC(msm_run(ctx, count, &res));
-    return compress_or_park(ctx, res, off, count, d_status, d_out, dc);
+    return msm_and_compress(ctx, off, count, d_status, d_out, dc);
 }
 
 // device pointers handed to the *_device entry points are read with 128-bit loads

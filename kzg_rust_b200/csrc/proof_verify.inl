@@ -71,10 +71,8 @@ static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t 
     ctx->launches++;
     RC(rc);
     RC(msm_digits_from_scalars(ctx, ln->d_inv, count));  // the quotient, canonical, where the inverses were
-    const g1_affine_t *res = nullptr;
-    RC(msm_run(ctx, count, &res));
-    if (side) CU(cudaStreamWaitEvent(st, ln->ev_side_join, 0));  // the compression reads the status the check wrote
-    return compress_or_park(ctx, res, off, count, d_status, d_proofs, dc);
+    // the compression reads the status the check wrote: it waits for the side stream
+    return msm_and_compress(ctx, off, count, d_status, d_proofs, dc, side ? ln->ev_side_join : nullptr);
 }
 
 extern "C" int kzg_b200_compute_blob_kzg_proof_device(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t *d_commitments,

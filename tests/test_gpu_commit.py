@@ -251,3 +251,41 @@ def test_automatic_comb_width_follows_the_memory_rule():
         s.close()
     # 9 GB cannot hold a table beside the fixed scratch of the addition kernel: the rule stops at its floor (8), not at 2
     assert widths == sorted(widths, reverse=True) and widths[2] >= 16 and widths[-1] >= 8, widths
+
+
+@pytest.mark.parametrize("preset", ["mainnet", "minimal"])
+def test_small_batch_form_equals_the_batched_affine_tree(preset):
+    """Batches of up to 64 blobs sum the table entries with one warp per sum in Jacobian coordinates (csrc/msm.cu:
+    k_comb_rows_warp) instead of the batched affine levels: the same 48 bytes, for commitments and proofs, including blobs
+    whose sums cancel (all zero, all r - 1, two equal rows) and the vectors of the reference."""
+    k = _kzg()
+    s = gpu_settings(preset, 8)
+    n = 4096 if preset == "mainnet" else 4
+    blobs = synthetic_blobs(64, n=n, seed=0x5A11).copy()
+    blobs[3] = 0
+    blobs[7] = np.tile(np.frombuffer((R - 1).to_bytes(32, "big"), dtype=np.uint8), n)
+    blobs[9] = np.tile(np.frombuffer((1).to_bytes(32, "big"), dtype=np.uint8), n)
+    blobs[11] = blobs[10]
+    if preset == "mainnet":
+        good = [c for c in G.by_fn("blob_to_kzg_commitment") if c["output"] is not None]
+        for i, c in enumerate(good):
+            blobs[20 + i] = np.frombuffer(G.get_bytes(c["input"]["blob"]), dtype=np.uint8)
+    outs = {}
+    for small_max in (64, 0):
+        os.environ["KZG_B200_MSM_SMALL_MAX"] = str(small_max)
+        try:
+            res = []
+            for m in (1, 5, 64):
+                cms, st = k.Kzg.blob_to_kzg_commitment_batch(blobs[:m], s)
+                assert not st.any()
+                prs, st = k.Kzg.compute_blob_kzg_proof_batch(blobs[:m], cms, s)
+                assert not st.any()
+                res.append((cms.tobytes(), prs.tobytes()))
+            outs[small_max] = res
+        finally:
+            del os.environ["KZG_B200_MSM_SMALL_MAX"]
+    assert outs[64] == outs[0]
+    if preset == "mainnet":
+        cms = np.frombuffer(outs[64][2][0], dtype=np.uint8).reshape(64, 48)
+        for i, c in enumerate(good):
+            assert "0x" + cms[20 + i].tobytes().hex() == c["output"]
