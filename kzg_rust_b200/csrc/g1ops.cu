@@ -78,8 +78,8 @@ __global__ void __launch_bounds__(64) k_horner_compress(const g1_affine_t *sums,
         o[k] = (uint32_t)buf[4 * k] | ((uint32_t)buf[4 * k + 1] << 8) | ((uint32_t)buf[4 * k + 2] << 16) | ((uint32_t)buf[4 * k + 3] << 24);
 }
 // The same with one WARP per blob, for small batches where the pass is pure latency (254 dependent doublings and
-// additions per blob, 4.5 ms): lane k folds the sums 8k .. 8k + 7, then five rounds join the 32 partial results,
-// T_k + 2^(8 s) T_(k + s) -- the doublings stay on the critical path (255 of them), the additions leave it (12
+// additions per blob, 4.5 ms): lane k folds the sums 8k .. 8k + 7 (W = 255; 2k, 2k + 1 for the 64 sums of the latency
+// comb), then five rounds join the 32 partial results, T_k + 2^(8 s) T_(k + s) -- the doublings stay on the critical path (255 of them), the additions leave it (12
 // instead of 254), and from the second round on three lanes share every doubling.
 #define KZG_HORNER_WARP_MAX 1024
 // JAC: the sums are Jacobian points (the small-batch form of the MSM, msm_run_small), canonical.
@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(128) k_horner_compress_warp(const void *sums_v
         if (lane < 12) o[lane] = 0;
         return;
     }
-    const int lo = 8 * (int)lane, hi = min(lo + 8, W);
+    const int rpl = (W + 31) / 32;  // sums per lane: 8 for the 255 sums of the comb, 2 for the 64 of the latency comb
+    const int lo = rpl * (int)lane, hi = min(lo + rpl, W);
     g1_jac_t acc;
     g1j_set_inf(acc);
 #pragma unroll 1
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(128) k_horner_compress_warp(const void *sums_v
             if (role == 0) {
                 g1_jac_t t = part[warp][lane + s];
 #pragma unroll 1
-                for (uint32_t d = 0; d < 8 * s; d++) g1j_dbl(t, t);
+                for (uint32_t d = 0; d < (uint32_t)rpl * s; d++) g1j_dbl(t, t);
                 g1_jac_t a = part[warp][lane];
                 g1j_add(t, t, a);
                 part[warp][lane] = t;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(128) k_horner_compress_warp(const void *sums_v
             // its 8 s doublings (g1j_dbl_n_coop3, g1.cuh) -- 240 of the 248 doublings of the critical path
             const uint32_t mask = s == 2 ? 0x77777777u : s == 4 ? 0x07070707u : s == 8 ? 0x00070007u : 0x00000007u;
             g1_jac_t t = part[warp][(lane - role) + s];
-            g1j_dbl_n_coop3(t, 8 * s, mask, (int)(lane - role), (int)role);
+            g1j_dbl_n_coop3(t, (uint32_t)rpl * s, mask, (int)(lane - role), (int)role);
             if (role == 0) {
                 g1_jac_t a = part[warp][lane];
                 g1j_add(t, t, a);

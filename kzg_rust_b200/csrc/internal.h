@@ -61,6 +61,12 @@ struct kzg_b200_ctx {
     int grid_blocks = 3;  // blocks per SM a launch asks for (KZG_B200_GRID_BLOCKS)
     kzg::g1_affine_t *d_table = nullptr;
     kzg::g1_affine_t *d_bases = nullptr;  // the n_pad setup points, bit-reversal permuted (src/kzg.rs:895-896)
+    // The latency comb (mainnet, optional): the Horner pass of a commitment is 255 dependent doublings -- most of what a
+    // small call takes.  A second, small table over the 4 n "virtual" points 2^(64 t) G_i (t < 4; groups of 16, 2^15 entries
+    // each, 3.2 GB) lets bit positions j, j + 64, j + 128, j + 192 share one sum: 64 sums of 1024 entries and 63 doublings
+    // per commitment.  Used by single-chunk calls of up to KZG_MSM_SMALL_MAX blobs (msm_run_latency).
+    kzg::g1_affine_t *d_table_lat = nullptr;
+    kzg::g1_affine_t *d_bases_lat = nullptr;  // [t][i] = 2^(64 t) bases[i]
     kzg::fr_t *d_roots = nullptr;         // roots of unity, Montgomery form, bit-reversed (src/kzg.rs:764-799)
     uint8_t g2_tau[96];                   // [tau]G2 = g2_values[1]
     // Work is cut into chunks of `chunk` blobs.  Two chunks are in flight at a time, each on its
@@ -160,6 +166,16 @@ int msm_run(kzg_b200_ctx *ctx, size_t count, const kzg::g1_affine_t **out);
 #define KZG_MSM_SMALL_CAP 64
 int msm_run_small(kzg_b200_ctx *ctx, size_t count, const kzg::g1_jac_t **out);
 bool msm_small_fits(const kzg_b200_ctx *ctx, size_t count);
+// the latency comb: KZG_LAT_T virtual points per setup point, groups of KZG_LAT_G, KZG_LAT_ROWS sums per blob
+#define KZG_LAT_G 16
+#define KZG_LAT_T 4
+#define KZG_LAT_ROWS 64
+size_t msm_latency_table_bytes(const kzg_b200_ctx *ctx);
+// builds ctx->d_table_lat / d_bases_lat (both allocated by the caller) from ctx->d_bases; needs the lane workspace
+int msm_build_latency_table(kzg_b200_ctx *ctx);
+// the KZG_LAT_ROWS sums of every blob from the sign words of the current lane, Jacobian, (*out)[j*count + b]
+int msm_run_latency(kzg_b200_ctx *ctx, size_t count, const kzg::g1_jac_t **out);
+bool msm_latency_ok(const kzg_b200_ctx *ctx, size_t count);
 // bytes of lane workspace the MSM needs per blob of a chunk
 size_t msm_workspace_per_blob(const kzg_b200_ctx *ctx);
 int msm_alloc_lane(kzg_b200_ctx *ctx, kzg_b200_ctx::Lane &ln, size_t chunk);

@@ -182,6 +182,22 @@ static int ctx_init(kzg_b200_ctx *ctx, const uint8_t *g1_lagrange, size_t n1, co
     const size_t usable = free_b > fixed + ((size_t)1 << 30) ? free_b - fixed : free_b / 2;
     const size_t chunk = std::max<size_t>(1, std::min(chunk_cap, usable / per_blob_workspace(ctx)));
     RC(alloc_workspace(ctx, chunk));
+    // the latency comb of small calls (internal.h), when it fits beside everything else: not fatal if it does not
+    if (n1 % KZG_LAT_G == 0 && n1 >= 64 && env_int("KZG_B200_LATENCY_TABLE", 1) != 0) {
+        const size_t lat = msm_latency_table_bytes(ctx) + (size_t)KZG_LAT_T * n1 * sizeof(g1_affine_t);
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t used = table_bytes(n1, g) + chunk * per_blob_workspace(ctx) + scratch_bytes(ctx);
+        if (lat + reserve <= free_b && (!budget || used + lat + reserve <= budget)) {
+            if (cudaMalloc(&ctx->d_table_lat, msm_latency_table_bytes(ctx)) == cudaSuccess &&
+                cudaMalloc(&ctx->d_bases_lat, (size_t)KZG_LAT_T * n1 * sizeof(g1_affine_t)) == cudaSuccess) {
+                RC(msm_build_latency_table(ctx));
+            } else {
+                (void)cudaGetLastError();
+                cudaFree(ctx->d_table_lat);
+                ctx->d_table_lat = nullptr;
+            }
+        }
+    }
     return KZG_B200_OK;
 }
 
@@ -253,6 +269,8 @@ extern "C" void kzg_b200_ctx_destroy(kzg_b200_ctx *ctx) {
     for (cudaEvent_t e : ctx->ev_chunks) cudaEventDestroy(e);
     cudaFree(ctx->d_z_all);
     cudaFree(ctx->d_sums_all);
+    cudaFree(ctx->d_table_lat);
+    cudaFree(ctx->d_bases_lat);
     cudaFree(ctx->d_table);
     cudaFree(ctx->d_bases);
     cudaFree(ctx->d_roots);
@@ -378,10 +396,13 @@ static int msm_and_compress(kzg_b200_ctx *ctx, size_t off, size_t count, const i
     const size_t small_max = (size_t)std::max(0, std::min(KZG_MSM_SMALL_CAP, env_int("KZG_B200_MSM_SMALL_MAX", KZG_MSM_SMALL_MAX)));
     if (count <= small_max && !(dc && dc->sums) && msm_small_fits(ctx, count)) {
         const g1_jac_t *sums = nullptr;
-        RC(msm_run_small(ctx, count, &sums));
+        // with the latency comb (internal.h): 64 sums and 63 doublings per blob instead of 255 and 254
+        const bool lat = msm_latency_ok(ctx, count) && env_int("KZG_B200_LATENCY_TABLE", 1) != 0;
+        if (lat) RC(msm_run_latency(ctx, count, &sums));
+        else RC(msm_run_small(ctx, count, &sums));
         if (join) CU(cudaStreamWaitEvent(st, join, 0));
         stage_begin(ctx, KZG_B200_STAGE_COMPRESS);
-        int rc = g1_launch_horner_compress_jac(st, sums, count, ctx->W, d_status, d_out, count);
+        int rc = g1_launch_horner_compress_jac(st, sums, count, lat ? KZG_LAT_ROWS : ctx->W, d_status, d_out, count);
         stage_end(ctx, 1);
         ctx->launches++;
         return rc;

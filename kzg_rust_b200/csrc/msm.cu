@@ -106,6 +106,101 @@ __global__ void __launch_bounds__(128) k_comb_rows_warp(const g1_affine_t *__res
     if (lane == 0) out[r] = acc;
 }
 
+// ---- the latency comb (internal.h): virtual points, digits, one block per sum
+// out[t*n + i] = 2^(64 t) bases[i], affine canonical
+__global__ void k_latency_bases(const g1_affine_t *__restrict__ bases, uint32_t n, g1_affine_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const g1_affine_t p = bases[i];
+    out[i] = p;
+    g1_jac_t q;
+    g1j_from_affine(q, p);
+#pragma unroll 1
+    for (uint32_t t = 1; t < KZG_LAT_T; t++) {
+#pragma unroll 1
+        for (int d = 0; d < 256 / KZG_LAT_T; d++) g1j_dbl(q, q);
+        g1_affine_t a;
+        g1j_to_affine(a, q);
+        out[(uint64_t)t * n + i] = a;
+    }
+}
+// Thread = (blob b, group q of 16 virtual points 2^(64 t) G_i, i0 <= i < i0 + 16): the signs of virtual point (t, i) at
+// row j are bits 64 t + j of the 256-digit form of scalar i's sign words -- s = sum_{j < 256} e_j 2^j with e_255 = +1,
+// which differs from the 255-digit form (blobpath.cuh) in the top two bits only: e_254 flips and e_255 = the old e_254.
+//   digits[(q*64 + j)*count + b]
+__global__ void __launch_bounds__(128) k_comb_index_latency(const uint32_t *__restrict__ sign_words, uint32_t count, uint32_t n,
+                                                             int n_pad, uint32_t *__restrict__ digits) {
+    const uint32_t groups_per_t = n / KZG_LAT_G, G = KZG_LAT_T * groups_per_t;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (uint64_t)count * G) return;
+    const uint32_t q = (uint32_t)(tid / count), b = (uint32_t)(tid - (uint64_t)q * count);
+    const uint32_t t = q / groups_per_t, i0 = (q - t * groups_per_t) * KZG_LAT_G;
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+        const int w = 2 * (int)t + h;
+        const uint32_t *row = sign_words + ((uint64_t)b * 8 + w) * (uint64_t)n_pad + i0;
+        uint32_t a[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            uint32_t v = k < KZG_LAT_G ? row[k] : 0u;
+            if (w == 7) v = (v & 0x3fffffffu) | ((~v) & 0x40000000u) | ((v & 0x40000000u) << 1);
+            a[k] = v;
+        }
+        transpose32(a);  // a[tt] bit k = sign of point k at bit position 32 w + tt
+#pragma unroll
+        for (int tt = 0; tt < 32; tt++) {
+            const int j = 32 * h + tt;
+            digits[((uint64_t)q * KZG_LAT_ROWS + j) * count + b] = comb_digit(a[tt], KZG_LAT_G);
+        }
+    }
+}
+// One BLOCK of four warps per sum (R = count x 64 blocks): thread l adds the entries of groups l, l + 128, ... in Jacobian
+// coordinates, shuffle rounds join the lanes of a warp, thread 0 the four warps.
+__global__ void __launch_bounds__(128) k_comb_rows_block(const g1_affine_t *__restrict__ table, const uint32_t *__restrict__ digits,
+                                                          uint32_t G, uint64_t E, uint32_t R, g1_jac_t *__restrict__ out) {
+    __shared__ g1_jac_t part[4];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t r = blockIdx.x;
+    auto load = [&](uint32_t q, g1_affine_t &p) {
+        const uint32_t d = digits[(uint64_t)q * R + r];
+        const g1_affine_t *src = table + (uint64_t)q * E + (d & 0x7fffffffu);
+        ld_fp(p.x, &src->x);
+        ld_fp(p.y, &src->y);
+        if ((d >> 31) && !g1a_is_inf(p)) fe_neg(p.y, p.y);
+    };
+    g1_jac_t acc;
+    g1j_set_inf(acc);
+    g1_affine_t cur;
+    g1a_set_inf(cur);
+    if (threadIdx.x < G) load(threadIdx.x, cur);
+#pragma unroll 1
+    for (uint32_t q = threadIdx.x; q < G; q += 128) {
+        g1_affine_t nxt;
+        g1a_set_inf(nxt);
+        if (q + 128 < G) load(q + 128, nxt);
+        if (!g1a_is_inf(cur)) g1j_add_affine(acc, acc, cur.x, cur.y);
+        cur = nxt;
+    }
+#pragma unroll 1
+    for (int s = 16; s > 0; s >>= 1) {
+        g1_jac_t o;
+        o.x = fp_shfl(0xffffffffu, acc.x, (int)lane + s);
+        o.y = fp_shfl(0xffffffffu, acc.y, (int)lane + s);
+        o.z = fp_shfl(0xffffffffu, acc.z, (int)lane + s);
+        if ((int)lane < s) g1j_add(acc, acc, o);
+    }
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll 1
+        for (int w = 1; w < 4; w++) {
+            g1_jac_t o = part[w];
+            g1j_add(acc, acc, o);
+        }
+        out[r] = acc;
+    }
+}
+
 // ------------------------------------------------------------------ launches
 static int ensure_scratch(kzg_b200_ctx *ctx, size_t elems) {
     kzg_b200_ctx::Lane *ln = ctx->cur;
@@ -264,6 +359,47 @@ int msm_run_small(kzg_b200_ctx *ctx, size_t count, const g1_jac_t **out) {
     k_comb_rows_warp<<<blocks_for(R, 4), 128, 0, ln->stream>>>(ctx->d_table, ln->d_digits, (uint32_t)ctx->G, ctx->E, (uint32_t)R, sums);
     stage_end(ctx, 1);
     ctx->launches++;
+    CU(cudaGetLastError());
+    *out = sums;
+    return KZG_B200_OK;
+}
+
+size_t msm_latency_table_bytes(const kzg_b200_ctx *ctx) {
+    return (size_t)KZG_LAT_T * ctx->n / KZG_LAT_G * ((size_t)1 << (KZG_LAT_G - 1)) * sizeof(g1_affine_t);
+}
+int msm_build_latency_table(kzg_b200_ctx *ctx) {
+    const uint32_t n = (uint32_t)ctx->n, G = KZG_LAT_T * n / KZG_LAT_G;
+    ctx->cur = &ctx->lanes[0];
+    cudaStream_t st = ctx->stream;
+    k_latency_bases<<<blocks_for(n, 64), 64, 0, st>>>(ctx->d_bases, n, ctx->d_bases_lat);
+    k_seed_table<<<blocks_for(G, 128), 128, 0, st>>>(ctx->d_bases_lat, ctx->d_table_lat, G, KZG_LAT_G);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    for (int m = 1; m < KZG_LAT_G; m++) {
+        const uint64_t total = (uint64_t)G << (m - 1);
+        RC(launch_batch_add(ctx, CombLevelPolicy{ctx->d_table_lat, ctx->d_bases_lat, (uint32_t)KZG_LAT_G, (uint32_t)m, 1u}, total));
+        RC(launch_batch_add(ctx, CombLevelPolicy{ctx->d_table_lat, ctx->d_bases_lat, (uint32_t)KZG_LAT_G, (uint32_t)m, 0u}, total));
+    }
+    CU(cudaStreamSynchronize(st));
+    return KZG_B200_OK;
+}
+bool msm_latency_ok(const kzg_b200_ctx *ctx, size_t count) {  // table built; the digits and sums fit the lane's buffers
+    if (!ctx->d_table_lat || !msm_small_fits(ctx, count)) return false;
+    const uint64_t G = (uint64_t)KZG_LAT_T * ctx->n / KZG_LAT_G;
+    return (uint64_t)count * KZG_LAT_ROWS * G <= (uint64_t)ctx->chunk * ctx->W * ctx->G;
+}
+int msm_run_latency(kzg_b200_ctx *ctx, size_t count, const g1_jac_t **out) {
+    kzg_b200_ctx::Lane *ln = ctx->cur;
+    if (!msm_latency_ok(ctx, count)) return KZG_B200_BAD_ARGS;
+    const uint32_t n = (uint32_t)ctx->n, G = KZG_LAT_T * n / KZG_LAT_G;
+    const uint64_t R = (uint64_t)count * KZG_LAT_ROWS;
+    g1_jac_t *sums = reinterpret_cast<g1_jac_t *>(ln->d_buf_a);
+    stage_begin(ctx, KZG_B200_STAGE_MSM_GATHER);
+    k_comb_index_latency<<<blocks_for((uint64_t)count * G, 128), 128, 0, ln->stream>>>(ln->d_sign_words, (uint32_t)count, n, ctx->n_pad,
+                                                                                       ln->d_digits);
+    k_comb_rows_block<<<(unsigned)R, 128, 0, ln->stream>>>(ctx->d_table_lat, ln->d_digits, G, (uint64_t)1 << (KZG_LAT_G - 1), (uint32_t)R, sums);
+    stage_end(ctx, 2);
+    ctx->launches += 2;
     CU(cudaGetLastError());
     *out = sums;
     return KZG_B200_OK;

@@ -271,8 +271,11 @@ def test_small_batch_form_equals_the_batched_affine_tree(preset):
         for i, c in enumerate(good):
             blobs[20 + i] = np.frombuffer(G.get_bytes(c["input"]["blob"]), dtype=np.uint8)
     outs = {}
-    for small_max in (64, 0):
+    # (threshold of the small form, latency comb on / off): the latency comb (64 sums over the virtual points 2^(64 t) G_i,
+    # csrc/internal.h) is the default of small mainnet calls, the 255-sum warp form its fallback, 0 = the batched affine tree
+    for small_max, lat in ((64, 1), (64, 0), (0, 1)):
         os.environ["KZG_B200_MSM_SMALL_MAX"] = str(small_max)
+        os.environ["KZG_B200_LATENCY_TABLE"] = str(lat)
         try:
             res = []
             for m in (1, 5, 64):
@@ -281,11 +284,12 @@ def test_small_batch_form_equals_the_batched_affine_tree(preset):
                 prs, st = k.Kzg.compute_blob_kzg_proof_batch(blobs[:m], cms, s)
                 assert not st.any()
                 res.append((cms.tobytes(), prs.tobytes()))
-            outs[small_max] = res
+            outs[(small_max, lat)] = res
         finally:
             del os.environ["KZG_B200_MSM_SMALL_MAX"]
-    assert outs[64] == outs[0]
+            del os.environ["KZG_B200_LATENCY_TABLE"]
+    assert outs[(64, 1)] == outs[(0, 1)] and outs[(64, 0)] == outs[(0, 1)]
     if preset == "mainnet":
-        cms = np.frombuffer(outs[64][2][0], dtype=np.uint8).reshape(64, 48)
+        cms = np.frombuffer(outs[(64, 1)][2][0], dtype=np.uint8).reshape(64, 48)
         for i, c in enumerate(good):
             assert "0x" + cms[20 + i].tobytes().hex() == c["output"]
