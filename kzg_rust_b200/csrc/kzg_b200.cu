@@ -345,10 +345,11 @@ struct DeferredCompress {
     uint8_t *out = nullptr;       // n x 48 B and n x int32 of the whole call, for host-buffer calls (they come after `sums`)
     int32_t *status = nullptr;
 };
-static int deferred_begin(kzg_b200_ctx *ctx, size_t n, DeferredCompress *dc) {
+// several_pieces: the call runs as more than one chunk although it would fit one (host calls cut by msm_piece_plan)
+static int deferred_begin(kzg_b200_ctx *ctx, size_t n, DeferredCompress *dc, bool several_pieces = false) {
     dc->sums = nullptr;
     dc->n = n;
-    if (n <= ctx->chunk) return KZG_B200_OK;
+    if (n <= ctx->chunk && !several_pieces) return KZG_B200_OK;
     const size_t elems = n * (size_t)ctx->W + n;  // + n x 96 B: room for the call's outputs (48 B) and status words
     if (elems > ctx->sums_all_elems) {
         if (ctx->d_sums_all) CU(cudaFree(ctx->d_sums_all));
@@ -449,11 +450,26 @@ extern "C" int kzg_b200_blob_to_kzg_commitment_device(kzg_b200_ctx *ctx, const u
 // upload(slot, off, cnt) enqueues the H2D copies of one chunk on copy_stream; run(slot, off, cnt)
 // enqueues kernels + D2H on the current lane's stream.
 // finish() runs once after the lanes have joined, on the caller-visible stream, before the call waits for it.
-// piece: blobs per chunk of this call (at most ctx->chunk, the size of a staging slot).
+// piece: blobs per chunk of this call (at most ctx->chunk, the size of a staging slot); first: blobs of the first chunk
+// (0 = like the others) -- nothing overlaps the upload of the first chunk, so it should be short.
+struct PiecePlan { size_t first, piece; };
+// Commitment / proof calls over host buffers.  A call that fits one chunk is cut in two halves from 512 blobs on (the second
+// half uploads under the first one's kernels and the two lanes overlap: 1,024 blobs 18.3 -> 16.6 ms, 4,096 blobs 67.8 -> 58 ms,
+// profiles/mid_chunks_r2as.txt); a larger call starts with a 1,024-blob chunk (2.5 ms of exposed upload instead of 10).
+static PiecePlan msm_piece_plan(const kzg_b200_ctx *ctx, size_t n) {
+    const size_t ch = ctx->chunk;
+    if (env_int("KZG_B200_PLAIN_PIECES", 0)) return {0, ch};
+    if (n <= ch) return n >= 512 ? PiecePlan{0, (n + 1) / 2} : PiecePlan{0, ch};
+    return {std::min<size_t>(ch, 1024), ch};
+}
 template <class Upload, class Run, class Finish>
-static int staged_chunks(kzg_b200_ctx *ctx, size_t n, size_t piece, Upload upload, Run run, Finish finish) {
+static int staged_chunks(kzg_b200_ctx *ctx, size_t n, size_t piece, Upload upload, Run run, Finish finish, size_t first = 0) {
     piece = std::max<size_t>(1, std::min(piece, ctx->chunk));
-    const size_t nchunks = (n + piece - 1) / piece;
+    if (first == 0 || first > piece) first = piece;
+    first = std::min(first, n);
+    const size_t nchunks = n <= first ? 1 : 1 + (n - first + piece - 1) / piece;
+    auto piece_off = [&](size_t i) { return i == 0 ? (size_t)0 : first + (i - 1) * piece; };
+    auto piece_cnt = [&](size_t i) { return i == 0 ? first : std::min(piece, n - piece_off(i)); };
     const size_t ahead = KZG_SLOTS - 1;
     ctx->call_blobs = n;
     const bool trace = env_int("KZG_B200_TRACE", 0) == 2;  // host wall clock of the enqueue / wait phases on stderr
@@ -466,7 +482,7 @@ static int staged_chunks(kzg_b200_ctx *ctx, size_t n, size_t piece, Upload uploa
     };
     auto enqueue_upload = [&](size_t i) -> int {
         int slot = (int)(i % KZG_SLOTS);
-        size_t off = i * piece, cnt = std::min(piece, n - off);
+        size_t off = piece_off(i), cnt = piece_cnt(i);
         CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[slot], 0));  // the chunk that used this slot is done
         ctx->aux_recorded[slot] = false;
         ctx->slices_recorded[slot] = 0;
@@ -481,7 +497,7 @@ static int staged_chunks(kzg_b200_ctx *ctx, size_t n, size_t piece, Upload uploa
     lap("uploads");
     for (size_t i = 0; i < nchunks; i++) {
         int slot = (int)(i % KZG_SLOTS);
-        size_t off = i * piece, cnt = std::min(piece, n - off);
+        size_t off = piece_off(i), cnt = piece_cnt(i);
         if (i + ahead < nchunks) RC(enqueue_upload(i + ahead));
         lane_select(ctx, i);
         // a sliced upload is waited for slice by slice by the chunk itself (verify_chunk_a); its last slice event is ev_h2d's equal
@@ -504,8 +520,8 @@ static int staged_chunks(kzg_b200_ctx *ctx, size_t n, size_t piece, Upload uploa
     return KZG_B200_OK;
 }
 template <class Upload, class Run>
-static int staged_chunks(kzg_b200_ctx *ctx, size_t n, size_t piece, Upload upload, Run run) {
-    return staged_chunks(ctx, n, piece, upload, run, []() -> int { return KZG_B200_OK; });
+static int staged_chunks(kzg_b200_ctx *ctx, size_t n, size_t piece, Upload upload, Run run, size_t first = 0) {
+    return staged_chunks(ctx, n, piece, upload, run, []() -> int { return KZG_B200_OK; }, first);
 }
 // grow-only pinned host buffer of the context (results that the host reads while the GPU works on the next chunk)
 static int ensure_pinned(kzg_b200_ctx *ctx, size_t bytes) {
@@ -526,9 +542,10 @@ extern "C" int kzg_b200_blob_to_kzg_commitment_batch(kzg_b200_ctx *ctx, const ui
     const size_t bpb = (size_t)ctx->n * 32, ch = ctx->chunk;
     // calls over several chunks run the Horner + compression pass once at the end, like the device-resident form
     DeferredCompress dc;
-    RC(deferred_begin(ctx, n, &dc));
+    const PiecePlan plan = msm_piece_plan(ctx, n);
+    RC(deferred_begin(ctx, n, &dc, n > std::min(plan.piece, ctx->chunk)));
     return staged_chunks(
-        ctx, n, ch,
+        ctx, n, plan.piece,
         [&](int slot, size_t off, size_t cnt) -> int {
             CU(cudaMemcpyAsync(ctx->d_stage_in + slot * ch * bpb, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->copy_stream));
             return KZG_B200_OK;
@@ -549,7 +566,8 @@ extern "C" int kzg_b200_blob_to_kzg_commitment_batch(kzg_b200_ctx *ctx, const ui
             CU(cudaMemcpyAsync(out, dc.out, n * 48, cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaMemcpyAsync(status, dc.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
             return KZG_B200_OK;
-        });
+        },
+        plan.first);
 }
 
 // ------------------------------------------------------------------ roofline micro-benchmarks, test aids

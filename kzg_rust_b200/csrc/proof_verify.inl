@@ -125,9 +125,10 @@ extern "C" int kzg_b200_compute_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const ui
     CU(cudaSetDevice(ctx->device));
     const size_t bpb = (size_t)ctx->n * 32, ch = ctx->chunk;
     DeferredCompress dc;
-    RC(deferred_begin(ctx, n, &dc));
+    const PiecePlan plan = msm_piece_plan(ctx, n);
+    RC(deferred_begin(ctx, n, &dc, n > std::min(plan.piece, ctx->chunk)));
     return staged_chunks(
-        ctx, n, ch,
+        ctx, n, plan.piece,
         [&](int slot, size_t off, size_t cnt) -> int {
             CU(cudaMemcpyAsync(ctx->d_stage_aux + slot * ch * 96, commitments + off * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->copy_stream));
             CU(cudaEventRecord(ctx->ev_aux[slot], ctx->copy_stream));
@@ -152,7 +153,8 @@ extern "C" int kzg_b200_compute_blob_kzg_proof_batch(kzg_b200_ctx *ctx, const ui
             CU(cudaMemcpyAsync(proofs_out, dc.out, n * 48, cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaMemcpyAsync(status, dc.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
             return KZG_B200_OK;
-        });
+        },
+        plan.first);
 }
 
 extern "C" int kzg_b200_compute_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t *blobs, const uint8_t *z, size_t n,
@@ -162,8 +164,9 @@ extern "C" int kzg_b200_compute_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t
     CU(cudaSetDevice(ctx->device));
     const size_t bpb = (size_t)ctx->n * 32, ch = ctx->chunk;
     std::vector<uint8_t> zy(n * 64);
+    const PiecePlan plan = msm_piece_plan(ctx, n);
     RC(staged_chunks(
-        ctx, n, ch,
+        ctx, n, plan.piece,
         [&](int slot, size_t off, size_t cnt) -> int {
             CU(cudaMemcpyAsync(ctx->d_stage_in + slot * ch * bpb, blobs + off * bpb, cnt * bpb, cudaMemcpyHostToDevice, ctx->copy_stream));
             CU(cudaMemcpyAsync(ctx->d_stage_aux + slot * ch * 96, z + off * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -177,7 +180,8 @@ extern "C" int kzg_b200_compute_kzg_proof_batch(kzg_b200_ctx *ctx, const uint8_t
             CU(cudaMemcpyAsync(zy.data() + off * 64, ctx->cur->d_zy, cnt * 64, cudaMemcpyDeviceToHost, ctx->cur->stream));
             CU(cudaMemcpyAsync(status + off, d_st, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->cur->stream));
             return KZG_B200_OK;
-        }));
+        },
+        plan.first));
     for (size_t i = 0; i < n; i++) {
         if (status[i] == KZG_B200_OK) memcpy(y_out + i * 32, zy.data() + 64 * i + 32, 32);
         else memset(y_out + i * 32, 0, 32);

@@ -293,3 +293,32 @@ def test_small_batch_form_equals_the_batched_affine_tree(preset):
         cms = np.frombuffer(outs[(64, 1)][2][0], dtype=np.uint8).reshape(64, 48)
         for i, c in enumerate(good):
             assert "0x" + cms[20 + i].tobytes().hex() == c["output"]
+
+
+def test_piece_plan_of_host_calls_gives_the_same_bytes():
+    """Host-buffer calls that fit one chunk are cut in two halves from 512 blobs on, larger ones start with a 1,024-blob
+    chunk (csrc/kzg_b200.cu: msm_piece_plan): commitments, blob proofs and proofs at given points equal those of the plain
+    chunking, on the benchmarked configuration (4,096-blob chunks)."""
+    k = _kzg()
+    s = gpu_settings("mainnet", 0)
+    n = 5000
+    blobs = synthetic_blobs(n, seed=0x91EC)
+    zs = synthetic_blobs(1, n=n, seed=0x91ED).reshape(n, 32)
+    outs = {}
+    for plain in (0, 1):
+        os.environ["KZG_B200_PLAIN_PIECES"] = str(plain)
+        try:
+            res = []
+            for m in (600, 1025, n):
+                cms, st = k.Kzg.blob_to_kzg_commitment_batch(blobs[:m], s)
+                assert not st.any()
+                prs, st = k.Kzg.compute_blob_kzg_proof_batch(blobs[:m], cms, s)
+                assert not st.any()
+                res.append((cms.tobytes(), prs.tobytes()))
+            pz, ys, st = k.Kzg.compute_kzg_proof_batch(blobs[:700], zs[:700], s)
+            assert not st.any()
+            res.append((pz.tobytes(), ys.tobytes()))
+            outs[plain] = res
+        finally:
+            del os.environ["KZG_B200_PLAIN_PIECES"]
+    assert outs[0] == outs[1]
