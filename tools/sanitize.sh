@@ -8,7 +8,7 @@ OUT=gpurun_out/sanitizer_$TAG.txt
 : > $OUT
 run() {
   echo "== compute-sanitizer --tool $1 :: $2 -k '$3'" | tee -a $OUT
-  timeout 1500 compute-sanitizer --tool $1 --error-exitcode 9 --print-limit 5 python -m pytest -x -q "$2" -k "$3" 2>&1 | grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY|Invalid|hazard|error" | tail -8 | tee -a $OUT
+  timeout 1500 compute-sanitizer --tool $1 --error-exitcode 9 --print-limit 5 python -m pytest -x -q "$2" -k "$3" 2>&1 | grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY|SYNCCHECK|Invalid|hazard|error|Barrier|divergent" | tail -8 | tee -a $OUT
 }
 run memcheck tests/test_gpu_commit.py "g8"
 run memcheck tests/test_gpu_proof.py "compute_blob_kzg_proof_vectors and g8"
@@ -19,3 +19,9 @@ run racecheck tests/test_gpu_proof.py "compute_blob_kzg_proof_vectors and g8"
 run memcheck tests/test_gpu_verify.py "bucket_method and (6 or 64 or 300)"
 run racecheck tests/test_gpu_verify.py "verify_blob_kzg_proof_batch_vectors and g8"
 run racecheck tests/test_gpu_verify.py "challenge_and_evaluation"
+# the small-call forms (latency comb, one warp / block per sum, three lanes per doubling: shuffles under partial masks) and
+# the sliced uploads with the state-carrying hash launches
+run memcheck tests/test_gpu_commit.py "small_batch_form and mainnet"
+run memcheck tests/test_gpu_verify.py "sliced_upload"
+run synccheck tests/test_gpu_commit.py "reference_vectors and g8"
+run synccheck tests/test_gpu_verify.py "verify_blob_kzg_proof_batch_vectors and g8"
