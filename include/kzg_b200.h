@@ -66,6 +66,9 @@ typedef struct kzg_b200_ctx kzg_b200_ctx;
  *                1..24; 0 = the widest comb whose table takes at most half of the device's free memory and
  *                leaves room for the workspace (23 on an empty 180 GB B200: 72 GB of table; 22: 38 GB, 4.5 % more
  *                additions; 20: 10 GB, 15 % more)
+ * A mainnet context also builds a second, 3.2 GB table for calls of up to 16 blobs (64 sums and 63 doublings per
+ * commitment instead of 255 and 254: a single blob_to_kzg_commitment in 0.75 ms) when it fits beside the first one, the
+ * workspace and the reserve; KZG_B200_LATENCY_TABLE=0 leaves it out.
  */
 int kzg_b200_ctx_create(const uint8_t *g1_lagrange, size_t n1, const uint8_t *g2_monomial, size_t n2,
                         int device, int comb_width, kzg_b200_ctx **out);
