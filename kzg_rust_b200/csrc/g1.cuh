@@ -388,6 +388,42 @@ KZG_HD bool g1a_in_subgroup(const g1_affine_t &p) {
     fe_neg(t, t);
     return fe_eq(t, q.y);
 }
+#if defined(__CUDACC__)
+// The same test by three lanes per point (leader, leader + 1, leader + 2; p on the leader): [x^2]P as [|x|]([|x|]P) --
+// |x| = 0xd201000000010000 has six set bits, so the two 64-bit multiplications are 126 doublings (shared by the three
+// lanes, g1j_dbl_n_coop3) and 10 additions where the 128-bit double-and-add over x^2 takes 127 and ~30.
+KZG_D void g1j_mul_x_coop3(g1_jac_t &r, const g1_jac_t &p, uint32_t mask, int leader, int role) {
+    g1_jac_t acc = p;
+    const uint32_t runs[6] = {1, 2, 3, 9, 32, 16};  // gaps between the set bits 63, 62, 60, 57, 48, 16, 0
+#pragma unroll 1
+    for (int i = 0; i < 6; i++) {
+        g1j_dbl_n_coop3(acc, runs[i], mask, leader, role);
+        if (i < 5 && role == 0) g1j_add(acc, acc, p);
+    }
+    r = acc;
+}
+KZG_D bool g1a_in_subgroup_coop3(const g1_affine_t &p, uint32_t mask, int leader, int role) {
+    g1_jac_t b, q;
+    b.x = p.x; b.y = p.y; b.z = fe_one<FpParams>();
+    g1j_mul_x_coop3(q, b, mask, leader, role);
+    g1j_mul_x_coop3(q, q, mask, leader, role);
+    if (role != 0 || g1j_is_inf(q)) return false;
+    fp_t beta, z2, z3, t;
+    {
+        constexpr uint32_t bm[12] = {FP_BETA_MONT_LIMBS};
+#pragma unroll
+        for (int i = 0; i < 12; i++) beta.l[i] = bm[i];
+    }
+    fe_sqr(z2, q.z);
+    fe_mul(z3, z2, q.z);
+    fe_mul(t, p.x, beta);
+    fe_mul(t, t, z2);
+    if (!fe_eq(t, q.x)) return false;
+    fe_mul(t, p.y, z3);
+    fe_neg(t, t);
+    return fe_eq(t, q.y);
+}
+#endif
 // the defining test, [r]P == infinity (kept for cross-checks)
 KZG_HD bool g1a_in_subgroup_by_order(const g1_affine_t &p) {
     uint32_t k[8];

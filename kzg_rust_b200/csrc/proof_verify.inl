@@ -465,7 +465,7 @@ static int verify_phase_b_locked(kzg_b200_ctx *ctx, const uint8_t *commitments, 
     // as the bucket method itself) run beside them on the side stream -- the sums of a point outside G1 are garbage, and the
     // call is rejected before anyone sees them.  verify_kzg_proof: 4.2 -> 3.1 ms.
     kzg_b200_ctx::Lane *ln = &ctx->lanes[0];
-    const bool beside = !ctx->profile && (2 * n + 127) / 128 <= (size_t)ctx->sms / 2;
+    const bool beside = !ctx->profile && (2 * n + 39) / 40 <= (size_t)ctx->sms / 2;  // ten points per warp, four warps per block
     stage_begin(ctx, KZG_B200_STAGE_VALIDATE);
     int rc = g1_launch_decode2(ctx->stream, vb.in_bytes, vb.in_bytes + 48 * n, vb.pts, vb.pts + n, vb.status, n, beside ? 0 : 1);
     stage_end(ctx, 1);
