@@ -2,6 +2,7 @@
 // kzg_rust_b200/csrc/bigint.cuh) to ctypes, so tests can compare them with Python ints.
 #include "../../kzg_rust_b200/csrc/fields.cuh"
 #include "../../tools/experiments/fp_hybrid.cuh"
+#include "../../tools/experiments/safegcd.cuh"
 using namespace kzg;
 extern "C" {
 void shim_fp_mul2(const uint32_t *a1, const uint32_t *b1, const uint32_t *a2, const uint32_t *b2, uint32_t *r1, uint32_t *r2) {
@@ -12,6 +13,10 @@ void shim_fp_mul2(const uint32_t *a1, const uint32_t *b1, const uint32_t *a2, co
 void shim_fp_mul(const uint32_t *a, const uint32_t *b, uint32_t *r) { fp_t x, y, z; memcpy(x.l, a, 48); memcpy(y.l, b, 48); fe_mul(z, x, y); memcpy(r, z.l, 48); }
 void shim_fp_add(const uint32_t *a, const uint32_t *b, uint32_t *r) { fp_t x, y, z; memcpy(x.l, a, 48); memcpy(y.l, b, 48); fe_add(z, x, y); memcpy(r, z.l, 48); }
 void shim_fp_sub(const uint32_t *a, const uint32_t *b, uint32_t *r) { fp_t x, y, z; memcpy(x.l, a, 48); memcpy(y.l, b, 48); fe_sub(z, x, y); memcpy(r, z.l, 48); }
+void shim_fp_inv_safegcd(const uint32_t *a, uint32_t *r) { fp_t x, z; memcpy(x.l, a, 48); fe_inv_safegcd(z, x); memcpy(r, z.l, 48); }
+void shim_fr_inv_safegcd(const uint32_t *a, uint32_t *r) { fr_t x, z; memcpy(x.l, a, 32); fe_inv_safegcd(z, x); memcpy(r, z.l, 32); }
+void shim_fp_inv_binary(const uint32_t *a, uint32_t *r) { fp_t x, z; memcpy(x.l, a, 48); fe_inv_binary(z, x); memcpy(r, z.l, 48); }
+void shim_fr_inv_binary(const uint32_t *a, uint32_t *r) { fr_t x, z; memcpy(x.l, a, 32); fe_inv_binary(z, x); memcpy(r, z.l, 32); }
 void shim_fp_inv(const uint32_t *a, uint32_t *r) { fp_t x, z; memcpy(x.l, a, 48); fp_inv(z, x); memcpy(r, z.l, 48); }
 int shim_fp_sqrt(const uint32_t *a, uint32_t *r) { fp_t x, z; memcpy(x.l, a, 48); bool ok = fp_sqrt(z, x); memcpy(r, z.l, 48); return ok; }
 int shim_fp_large(const uint32_t *a) { fp_t x; memcpy(x.l, a, 48); return fp_is_lexicographically_largest(x); }

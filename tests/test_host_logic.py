@@ -494,3 +494,35 @@ def test_bucket_method_of_phase_b_vs_ladders(msm, n, force_c):
         assert int.from_bytes(bytes(a)[96:128], "little") == s
         if force_c:
             assert c_used.value == force_c
+
+
+def test_divstep_inversion_vs_python(field):
+    """fe_inv_binary (csrc/bigint.cuh, the inversion of fp_inv / fr_inv) and fe_inv_safegcd (tools/experiments/safegcd.cuh:
+    Bernstein-Yang divsteps, 30 at a time -- measured on the GPU and not kept) against Python's pow(a, -1, m), on edge values (1, 2, m - 1, powers of two, runs of ones,
+    values just below the modulus), Fp inputs in [p, 2p) (the lazy residues the MSM's shared inversion hands over) and
+    random values."""
+    rng = np.random.default_rng(17)
+    for mod, n, fn, fn_bin in ((P, 12, field.shim_fp_inv_safegcd, field.shim_fp_inv_binary),
+                               (R, 8, field.shim_fr_inv_safegcd, field.shim_fr_inv_binary)):
+        bits = 32 * n
+        mont = pow(2, bits, mod)
+        vals = [1, 2, 3, mod - 1, mod - 2, (mod - 1) // 2, (mod + 1) // 2, 2 ** 30, 2 ** 30 - 1, 2 ** 60 + 1, 2 ** (mod.bit_length() - 1),
+                2 ** (mod.bit_length() - 1) - 1, 2 ** 200 - 1, (1 << 250) - (1 << 100), 0x5555555555555555555555555555555555555555555555555555555555555555 % mod,
+                mod - 2 ** 64, mod - 2 ** 30]
+        vals += [int.from_bytes(rng.bytes(n * 4), "big") % mod for _ in range(600)]
+        vals += [pow(3, k, mod) for k in range(1, 60)]
+        out, out2 = (ctypes.c_uint32 * n)(), (ctypes.c_uint32 * n)()
+        for a in vals:
+            if a % mod == 0:
+                continue
+            raw = a  # the integer handed over: a "Montgomery form" of a / 2^bits
+            fn(_limbs(raw, n), out)
+            want = pow(raw * pow(mont, -1, mod) % mod, -1, mod) * mont % mod
+            assert _val(out) == want, (hex(mod)[:10], hex(a))
+            fn_bin(_limbs(raw, n), out2)
+            assert _val(out2) == want
+        if n == 12:  # lazy residues: a + p < 2p
+            for a in vals[:40]:
+                raw = a + mod
+                fn(_limbs(raw, n), out)
+                assert _val(out) == pow(a * pow(mont, -1, mod) % mod, -1, mod) * mont % mod
