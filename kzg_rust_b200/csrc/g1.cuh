@@ -246,29 +246,62 @@ KZG_HD void g1j_mul(g1_jac_t &r, const g1_affine_t &p, const uint32_t *k, int nb
 // and the third table entry is free: P + psi(P) = -psi^2(P) = (beta x, -y).
 // Used by the r-power terms of batch verification, whose latency is one such ladder per blob.
 KZG_HD void glv_split(uint32_t k1[4], uint32_t k2[4], const uint32_t k[8]) {
-    // lambda = BLS_X_SQUARED - 1
+    // Barrett division by lambda = BLS_X_SQUARED - 1 (HAC 14.42, b = 2^32, four-limb modulus): mu = floor(2^256 / lambda),
+    // q = floor(floor(k / 2^96) mu / 2^160) is floor(k / lambda) or up to 2 less; the remainder is fixed up by subtraction.
+    // (A bit-serial long division stood here: 256 dependent rounds, most of k_pip_scalars' 80 us.)
     constexpr uint32_t xs[4] = {BLS_X_SQUARED_LIMBS};
     const uint32_t lam[5] = {xs[0] - 1u, xs[1] - (xs[0] == 0 ? 1u : 0u), xs[2], xs[3], 0u};  // low limb of x^2 is 0: borrow into limb 1
-    uint32_t rem[5] = {0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 1
-    for (int bit = 255; bit >= 0; bit--) {
-        // rem = 2 rem + bit  (rem < lambda before, so < 2^129 after)
+    constexpr uint32_t mu[5] = {0xf6cfee30u, 0x63f6e522u, 0xe01faaddu, 0x7c6becf1u, 0x00000001u};
+    uint32_t q2[10];
 #pragma unroll
-        for (int i = 4; i > 0; i--) rem[i] = (rem[i] << 1) | (rem[i - 1] >> 31);
-        rem[0] = (rem[0] << 1) | ((k[bit >> 5] >> (bit & 31)) & 1u);
-        uint32_t d[5], cc = 0;
-        d[0] = sub_cc(rem[0], lam[0], cc);
+    for (int i = 0; i < 10; i++) q2[i] = 0;
 #pragma unroll
-        for (int i = 1; i < 5; i++) d[i] = subc_cc(rem[i], lam[i], cc);
-        uint32_t borrow = subc(0, 0, cc);
-        if (borrow == 0) {
+    for (int i = 0; i < 5; i++) {  // q2 = (k >> 96) * mu
+        uint64_t c = 0;
 #pragma unroll
-            for (int i = 0; i < 5; i++) rem[i] = d[i];
-            q[bit >> 5] |= 1u << (bit & 31);
+        for (int j = 0; j < 5; j++) {
+            c += (uint64_t)k[3 + i] * mu[j] + q2[i + j];
+            q2[i + j] = (uint32_t)c;
+            c >>= 32;
+        }
+        q2[i + 5] = (uint32_t)c;
+    }
+    uint32_t q[5], r[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) { q[i] = q2[5 + i]; r[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 5; i++) {  // r = (q * lambda) mod 2^160
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j + i < 5; j++) {
+            c += (uint64_t)q[i] * lam[j] + r[i + j];
+            r[i + j] = (uint32_t)c;
+            c >>= 32;
         }
     }
+    {  // r = k - q lambda (mod 2^160): in [0, 3 lambda)
+        uint32_t cc = 0;
+        r[0] = sub_cc(k[0], r[0], cc);
 #pragma unroll
-    for (int i = 0; i < 4; i++) { k1[i] = rem[i]; k2[i] = q[i]; }  // q < 2^128 for k < 2^255 (r / lambda < 2^128)
+        for (int i = 1; i < 5; i++) r[i] = subc_cc(k[i], r[i], cc);
+    }
+#pragma unroll 1
+    for (int it = 0; it < 2; it++) {
+        uint32_t d[5], cc = 0;
+        d[0] = sub_cc(r[0], lam[0], cc);
+#pragma unroll
+        for (int i = 1; i < 5; i++) d[i] = subc_cc(r[i], lam[i], cc);
+        const uint32_t borrow = subc(0, 0, cc);
+        if (borrow != 0) break;
+#pragma unroll
+        for (int i = 0; i < 5; i++) r[i] = d[i];
+        uint32_t c2 = 0;
+        q[0] = add_cc(q[0], 1u, c2);
+#pragma unroll
+        for (int i = 1; i < 5; i++) q[i] = addc_cc(q[i], 0u, c2);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { k1[i] = r[i]; k2[i] = q[i]; }  // q < 2^128 for k < 2^255 (r / lambda < 2^128)
 }
 KZG_HD void g1j_mul_glv(g1_jac_t &r, const g1_affine_t &p, const uint32_t *k) {
     g1_jac_t acc;

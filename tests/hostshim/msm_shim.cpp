@@ -126,6 +126,7 @@ extern "C" void shim_sign_words(const uint32_t *scalar, uint32_t *out) {
 extern "C" uint32_t shim_comb_digit(uint32_t pattern, int g) { return comb_digit(pattern, g); }
 extern "C" void shim_transpose32(uint32_t *a) { transpose32(a); }
 // [k]P by the plain ladder and by the GLV ladder (g1.cuh), both compressed; k = 8 little-endian words
+extern "C" void shim_glv_split(const uint32_t *k, uint32_t *k1k2) { glv_split(k1k2, k1k2 + 4, k); }
 extern "C" int shim_g1_mul_both(const uint8_t *point48, const uint32_t *k, uint8_t *out_plain, uint8_t *out_glv, uint32_t *k1k2) {
     g1_affine_t p;
     if (!g1a_uncompress(p, point48)) return KZG_BADARGS;

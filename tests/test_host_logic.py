@@ -526,3 +526,20 @@ def test_divstep_inversion_vs_python(field):
                 raw = a + mod
                 fn(_limbs(raw, n), out)
                 assert _val(out) == pow(a * pow(mont, -1, mod) % mod, -1, mod) * mont % mod
+
+
+def test_glv_split_is_exact_division(msm):
+    """glv_split (csrc/g1.cuh: Barrett division by lambda, two fix-up subtractions at most) equals divmod on random scalars
+    and on the values where an estimate of the quotient is most likely to be off (multiples of lambda and their neighbours,
+    all-ones words, the largest scalars)."""
+    lam = 0xd201000000010000 ** 2 - 1
+    rng = np.random.default_rng(33)
+    ks = [0, 1, lam - 1, lam, lam + 1, R - 1, R - 2, 2 ** 255 - 1, 2 ** 254, 2 ** 128, 2 ** 128 - 1, 2 ** 160 - 1, 2 ** 224 - 1]
+    for m in (1, 2, 3, 2 ** 32 - 1, 2 ** 32, 2 ** 64 - 1, 2 ** 96, 2 ** 126, 2 ** 127 - 1, (R - 1) // lam):
+        ks += [m * lam - 1, m * lam, m * lam + 1]
+    ks += [int.from_bytes(rng.bytes(32), "big") >> 1 for _ in range(20000)]
+    ks += [(int.from_bytes(rng.bytes(16), "big") * lam + d) % 2 ** 255 for d in (0, 1, lam - 1) for _ in range(2000)]
+    out = (ctypes.c_uint32 * 8)()
+    for k in ks:
+        msm.shim_glv_split(_limbs(k, 8), out)
+        assert (_val(out[0:4]), _val(out[4:8])) == (k % lam, k // lam), hex(k)
