@@ -154,8 +154,9 @@ static inline unsigned blocks_for(uint64_t total, unsigned tpb) { return (unsign
 int msm_build_table(kzg_b200_ctx *ctx, const uint8_t *g1_bytes);
 // scalars of `count` blobs -> comb digits in the current lane: from blob bytes (with the canonical check, status[b]
 // = BAD_ARGS for a blob with an element >= r) or from canonical limbs scalars[b*n + i]
-int msm_digits_from_blobs(kzg_b200_ctx *ctx, const uint8_t *d_blobs, size_t count, int32_t *d_status);
-int msm_digits_from_scalars(kzg_b200_ctx *ctx, const kzg::fr_t *d_scalars, size_t count);
+// signs_only: stop after the sign words (the latency comb of small calls builds its own digits from them)
+int msm_digits_from_blobs(kzg_b200_ctx *ctx, const uint8_t *d_blobs, size_t count, int32_t *d_status, bool signs_only = false);
+int msm_digits_from_scalars(kzg_b200_ctx *ctx, const kzg::fr_t *d_scalars, size_t count, bool signs_only = false);
 // the 255 sums S_j of `count` blobs from the digits of the current lane: (*out)[j*count + b] (lazy residues)
 int msm_run(kzg_b200_ctx *ctx, size_t count, const kzg::g1_affine_t **out);
 // the same sums for a small batch, one warp per sum, as Jacobian points (no inversions on the way): see k_comb_rows_warp

@@ -391,14 +391,20 @@ static int deferred_finish(kzg_b200_ctx *ctx, const DeferredCompress *dc, const 
 
 // The MSM of one chunk from the digits of the current lane, down to the compressed points (or the parked sums).
 // Small single-chunk calls take the one-warp-per-sum form (msm_run_small; KZG_B200_MSM_SMALL_MAX blobs, 0 = never).
+// which form the MSM of a chunk takes: 0 = batched affine levels, 1 = one warp per sum, 2 = the latency comb
+static int msm_form(const kzg_b200_ctx *ctx, size_t count, const DeferredCompress *dc) {
+    const size_t small_max = (size_t)std::max(0, std::min(KZG_MSM_SMALL_CAP, env_int("KZG_B200_MSM_SMALL_MAX", KZG_MSM_SMALL_MAX)));
+    if (count > small_max || (dc && dc->sums) || !msm_small_fits(ctx, count)) return 0;
+    return msm_latency_ok(ctx, count) && env_int("KZG_B200_LATENCY_TABLE", 1) != 0 ? 2 : 1;
+}
 static int msm_and_compress(kzg_b200_ctx *ctx, size_t off, size_t count, const int32_t *d_status, uint8_t *d_out,
                             const DeferredCompress *dc, cudaEvent_t join = nullptr) {
     cudaStream_t st = ctx->cur->stream;
-    const size_t small_max = (size_t)std::max(0, std::min(KZG_MSM_SMALL_CAP, env_int("KZG_B200_MSM_SMALL_MAX", KZG_MSM_SMALL_MAX)));
-    if (count <= small_max && !(dc && dc->sums) && msm_small_fits(ctx, count)) {
+    const int form = msm_form(ctx, count, dc);
+    if (form != 0) {
         const g1_jac_t *sums = nullptr;
         // with the latency comb (internal.h): 64 sums and 63 doublings per blob instead of 255 and 254
-        const bool lat = msm_latency_ok(ctx, count) && env_int("KZG_B200_LATENCY_TABLE", 1) != 0;
+        const bool lat = form == 2;
         if (lat) RC(msm_run_latency(ctx, count, &sums));
         else RC(msm_run_small(ctx, count, &sums));
         if (join) CU(cudaStreamWaitEvent(st, join, 0));
@@ -418,7 +424,7 @@ static int msm_and_compress(kzg_b200_ctx *ctx, size_t off, size_t count, const i
 static int commit_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, size_t count, uint8_t *d_out, int32_t *d_status,
                         size_t off = 0, const DeferredCompress *dc = nullptr) {
     CU(cudaMemsetAsync(d_status, 0, count * sizeof(int32_t), ctx->cur->stream));
-    RC(msm_digits_from_blobs(ctx, d_blobs, count, d_status));
+    RC(msm_digits_from_blobs(ctx, d_blobs, count, d_status, msm_form(ctx, count, dc) == 2));
     return msm_and_compress(ctx, off, count, d_status, d_out, dc);
 }
 

@@ -285,24 +285,24 @@ static int comb_index(kzg_b200_ctx *ctx, size_t count) {
     CU(cudaGetLastError());
     return KZG_B200_OK;
 }
-int msm_digits_from_blobs(kzg_b200_ctx *ctx, const uint8_t *d_blobs, size_t count, int32_t *d_status) {
+int msm_digits_from_blobs(kzg_b200_ctx *ctx, const uint8_t *d_blobs, size_t count, int32_t *d_status, bool signs_only) {
     kzg_b200_ctx::Lane *ln = ctx->cur;
     const uint64_t total = (uint64_t)count * ctx->n_pad;
     stage_begin(ctx, KZG_B200_STAGE_DIGITS);
     k_blob_sign_words<<<blocks_for(total, 256), 256, 0, ln->stream>>>(d_blobs, total, ctx->n, ctx->n_pad, ln->d_sign_words, d_status);
     ctx->launches++;
-    int rc = comb_index(ctx, count);
-    stage_end(ctx, 2);
+    int rc = signs_only ? KZG_B200_OK : comb_index(ctx, count);  // the latency comb indexes the sign words itself
+    stage_end(ctx, signs_only ? 1 : 2);
     return rc;
 }
-int msm_digits_from_scalars(kzg_b200_ctx *ctx, const fr_t *d_scalars, size_t count) {
+int msm_digits_from_scalars(kzg_b200_ctx *ctx, const fr_t *d_scalars, size_t count, bool signs_only) {
     kzg_b200_ctx::Lane *ln = ctx->cur;
     const uint64_t total = (uint64_t)count * ctx->n_pad;
     stage_begin(ctx, KZG_B200_STAGE_DIGITS);
     k_fr_sign_words<<<blocks_for(total, 256), 256, 0, ln->stream>>>(d_scalars, total, ctx->n, ctx->n_pad, ln->d_sign_words);
     ctx->launches++;
-    int rc = comb_index(ctx, count);
-    stage_end(ctx, 2);
+    int rc = signs_only ? KZG_B200_OK : comb_index(ctx, count);
+    stage_end(ctx, signs_only ? 1 : 2);
     return rc;
 }
 

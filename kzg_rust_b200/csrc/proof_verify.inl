@@ -70,7 +70,7 @@ static int proof_chunk(kzg_b200_ctx *ctx, const uint8_t *d_blobs, const uint8_t 
     stage_end(ctx, 1);
     ctx->launches++;
     RC(rc);
-    RC(msm_digits_from_scalars(ctx, ln->d_inv, count));  // the quotient, canonical, where the inverses were
+    RC(msm_digits_from_scalars(ctx, ln->d_inv, count, msm_form(ctx, count, dc) == 2));  // the quotient, canonical, where the inverses were
     // the compression reads the status the check wrote: it waits for the side stream
     return msm_and_compress(ctx, off, count, d_status, d_proofs, dc, side ? ln->ev_side_join : nullptr);
 }
