@@ -25,3 +25,6 @@ run memcheck tests/test_gpu_commit.py "small_batch_form and mainnet"
 run memcheck tests/test_gpu_verify.py "sliced_upload"
 run synccheck tests/test_gpu_commit.py "reference_vectors and g8"
 run synccheck tests/test_gpu_verify.py "verify_blob_kzg_proof_batch_vectors and g8"
+# the three-lane subgroup checks of phase B on new data (verify_kzg_proof; shuffles under a 30-lane mask)
+run memcheck tests/test_gpu_verify.py "verify_kzg_proof_vectors and g8"
+run synccheck tests/test_gpu_verify.py "verify_kzg_proof_vectors and g8"
