@@ -158,7 +158,11 @@ int msm_build_table(kzg_b200_ctx *ctx, const uint8_t *g1_bytes);
 int msm_digits_from_blobs(kzg_b200_ctx *ctx, const uint8_t *d_blobs, size_t count, int32_t *d_status, bool signs_only = false);
 int msm_digits_from_scalars(kzg_b200_ctx *ctx, const kzg::fr_t *d_scalars, size_t count, bool signs_only = false);
 // the 255 sums S_j of `count` blobs from the digits of the current lane: (*out)[j*count + b] (lazy residues)
-int msm_run(kzg_b200_ctx *ctx, size_t count, const kzg::g1_affine_t **out);
+// out_jac != nullptr: chunks of up to KZG_JAC_TAIL_MAX blobs may end with the Jacobian tail (k_tail_rows_jac, msm.cu): then
+// *out is null and *out_jac holds the sums as Jacobian points
+#define KZG_JAC_TAIL_MAX 256
+#define KZG_JAC_TAIL_ROWS 12
+int msm_run(kzg_b200_ctx *ctx, size_t count, const kzg::g1_affine_t **out, const kzg::g1_jac_t **out_jac = nullptr);
 // the same sums for a small batch, one warp per sum, as Jacobian points (no inversions on the way): see k_comb_rows_warp
 // default threshold: above ~16 blobs the sums no longer fit one wave of warps (255 per blob, eight resident per SM) and the
 // batched affine levels win (64 blobs: 2.97 ms against 1.79 ms; 1 blob: 0.16 against 0.85 ms); KZG_B200_MSM_SMALL_MAX moves

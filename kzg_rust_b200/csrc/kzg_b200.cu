@@ -415,8 +415,16 @@ static int msm_and_compress(kzg_b200_ctx *ctx, size_t off, size_t count, const i
         return rc;
     }
     const g1_affine_t *res = nullptr;
-    RC(msm_run(ctx, count, &res));
+    const g1_jac_t *jsums = nullptr;
+    RC(msm_run(ctx, count, &res, (dc && dc->sums) ? nullptr : &jsums));  // parked sums are affine
     if (join) CU(cudaStreamWaitEvent(st, join, 0));
+    if (jsums) {
+        stage_begin(ctx, KZG_B200_STAGE_COMPRESS);
+        int rc = g1_launch_horner_compress_jac(st, jsums, count, ctx->W, d_status, d_out, count);
+        stage_end(ctx, 1);
+        ctx->launches++;
+        return rc;
+    }
     return compress_or_park(ctx, res, off, count, d_status, d_out, dc);
 }
 

@@ -106,6 +106,36 @@ __global__ void __launch_bounds__(128) k_comb_rows_warp(const g1_affine_t *__res
     if (lane == 0) out[r] = acc;
 }
 
+// Mid-size batches: the last levels of the addition tree (12 -> 6 -> 3 -> 2 -> 1 rows) are four launches of few additions, each
+// around one shared inversion (~0.15 ms apiece whatever the size).  For chunks of up to KZG_JAC_TAIL_MAX blobs one thread per
+// sum adds the remaining rows in Jacobian coordinates instead (11 mixed additions, no inversion) and the warp Horner pass
+// takes the Jacobian sums.  in[q*R + r], q < rows: affine lazy residues.
+__global__ void __launch_bounds__(128) k_tail_rows_jac(const g1_affine_t *__restrict__ in, uint32_t rows, uint64_t R, g1_jac_t *__restrict__ out) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    g1_jac_t acc;
+    g1j_set_inf(acc);
+    g1_affine_t cur;
+    ld_fp(cur.x, &in[r].x);
+    ld_fp(cur.y, &in[r].y);
+#pragma unroll 1
+    for (uint32_t q = 0; q < rows; q++) {
+        g1_affine_t nxt;
+        g1a_set_inf(nxt);
+        if (q + 1 < rows) {
+            ld_fp(nxt.x, &in[(uint64_t)(q + 1) * R + r].x);
+            ld_fp(nxt.y, &in[(uint64_t)(q + 1) * R + r].y);
+        }
+        if (!g1a_is_inf(cur)) {
+            fe_canonical(cur.x);
+            fe_canonical(cur.y);
+            g1j_add_affine(acc, acc, cur.x, cur.y);
+        }
+        cur = nxt;
+    }
+    out[r] = acc;
+}
+
 // ---- the latency comb (internal.h): virtual points, digits, one block per sum
 // out[t*n + i] = 2^(64 t) bases[i], affine canonical
 __global__ void k_latency_bases(const g1_affine_t *__restrict__ bases, uint32_t n, g1_affine_t *__restrict__ out) {
@@ -306,7 +336,7 @@ int msm_digits_from_scalars(kzg_b200_ctx *ctx, const fr_t *d_scalars, size_t cou
     return rc;
 }
 
-int msm_run(kzg_b200_ctx *ctx, size_t count, const g1_affine_t **out) {
+int msm_run(kzg_b200_ctx *ctx, size_t count, const g1_affine_t **out, const g1_jac_t **out_jac) {
     kzg_b200_ctx::Lane *ln = ctx->cur;
     cudaStream_t st = ln->stream;
     const uint64_t R = (uint64_t)count * ctx->W;  // (bit position, blob) pairs = points per row of a level
@@ -332,7 +362,23 @@ int msm_run(kzg_b200_ctx *ctx, size_t count, const g1_affine_t **out) {
     g1_affine_t *in = ln->d_buf_a, *o = ln->d_buf_b;
     stage_begin(ctx, KZG_B200_STAGE_MSM_TREE);
     launches = 0;
+    // the Jacobian sums (144 B each) go into a tree buffer: the smaller one holds ceil(ceil(G / 2) / 2) rows of chunk x 255 points
+    const uint64_t small_buf = (uint64_t)ctx->chunk * (((uint64_t)(ctx->G + 1) / 2 + 1) / 2) * sizeof(g1_affine_t);
+    const bool jac_tail = out_jac != nullptr && count <= KZG_JAC_TAIL_MAX && (uint64_t)count * sizeof(g1_jac_t) <= small_buf &&
+                          env_int("KZG_B200_JAC_TAIL", 1) != 0;
+    if (out_jac) *out_jac = nullptr;
     while (rows > 1) {
+        if (jac_tail && rows <= KZG_JAC_TAIL_ROWS) {
+            g1_jac_t *sums = reinterpret_cast<g1_jac_t *>(o);  // R x 144 B in a buffer of at least 45 R x 96 B
+            k_tail_rows_jac<<<blocks_for(R, 128), 128, 0, st>>>(in, rows, R, sums);
+            launches++;
+            ctx->launches++;
+            CU(cudaGetLastError());
+            stage_end(ctx, launches);
+            *out = nullptr;
+            *out_jac = sums;
+            return KZG_B200_OK;
+        }
         PairPolicy tp{in, o, fd};
         RC(launch_batch_add(ctx, tp, R * (rows / 2)));
         launches++;

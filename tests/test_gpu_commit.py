@@ -322,3 +322,35 @@ def test_piece_plan_of_host_calls_gives_the_same_bytes():
         finally:
             del os.environ["KZG_B200_PLAIN_PIECES"]
     assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("width", VECTOR_WIDTHS, ids=VECTOR_WIDTH_IDS)
+def test_jacobian_tail_of_mid_size_batches_gives_the_same_bytes(width):
+    """Single-chunk calls of 17 .. 256 blobs end the addition tree at 12 rows and add the rest per sum in Jacobian coordinates
+    (csrc/msm.cu: k_tail_rows_jac): commitments and proofs equal those of the full affine tree, including blobs whose sums
+    cancel, and the first ones equal the oracle's."""
+    k = _kzg()
+    s = gpu_settings("mainnet", width)
+    o = oracle_settings("mainnet")
+    sizes = (17, 64, 128) if width != 0 else (40, 200, 256)
+    blobs = synthetic_blobs(max(sizes), seed=0x7A11).copy()
+    blobs[2] = 0
+    blobs[5] = np.tile(np.frombuffer((R - 1).to_bytes(32, "big"), dtype=np.uint8), 4096)
+    blobs[8] = blobs[7]
+    outs = {}
+    for tail in (1, 0):
+        os.environ["KZG_B200_JAC_TAIL"] = str(tail)
+        try:
+            res = []
+            for m in sizes:
+                cms, st = k.Kzg.blob_to_kzg_commitment_batch(blobs[:m], s)
+                assert not st.any()
+                prs, st = k.Kzg.compute_blob_kzg_proof_batch(blobs[:m], cms, s)
+                assert not st.any()
+                res.append((cms.tobytes(), prs.tobytes()))
+            outs[tail] = res
+        finally:
+            del os.environ["KZG_B200_JAC_TAIL"]
+    assert outs[1] == outs[0]
+    exp, est = o.blob_to_kzg_commitment_many(blobs[:12], nthreads=8)
+    assert not est.any() and outs[1][0][0][:12 * 48] == exp.tobytes()
